@@ -1,0 +1,165 @@
+// Forward-mode dual numbers used to linearize the discrete dynamics map.
+//
+// The reference obtains fx, fu by pushing n+m AutoDiffXd seeds through Drake's
+// discrete update (/root/reference/ilqr.py:253-270).  Here the same thing is
+// done in-kernel: the model's step() is a template on the scalar type, and the
+// Jacobian pass instantiates it with Dual<K>.  On the device the n+m seed
+// directions are spread over the G lanes of a lane-group (each lane carries K
+// of them; the value part is recomputed redundantly by every lane, which is
+// free in SIMT).  On the host the same template runs with K = n+m in one
+// thread, which is what the CPU oracle's dynamics shim calls.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define DDP_HD __host__ __device__ __forceinline__
+#else
+#define DDP_HD inline
+#endif
+
+namespace ddp {
+
+template <int K>
+struct Dual {
+  double v;
+  double d[K];
+  DDP_HD Dual() {}
+  DDP_HD Dual(double c) : v(c) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) d[k] = 0.0;
+  }
+};
+
+// ---- value extraction (for branches on contact state etc.) -----------------
+DDP_HD double val(double a) { return a; }
+template <int K>
+DDP_HD double val(const Dual<K>& a) { return a.v; }
+
+// ---- Dual (op) Dual ----------------------------------------------------------
+template <int K>
+DDP_HD Dual<K> operator+(const Dual<K>& a, const Dual<K>& b) {
+  Dual<K> r;
+  r.v = a.v + b.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = a.d[k] + b.d[k];
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator-(const Dual<K>& a, const Dual<K>& b) {
+  Dual<K> r;
+  r.v = a.v - b.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = a.d[k] - b.d[k];
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator*(const Dual<K>& a, const Dual<K>& b) {
+  Dual<K> r;
+  r.v = a.v * b.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = a.d[k] * b.v + a.v * b.d[k];
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator/(const Dual<K>& a, const Dual<K>& b) {
+  Dual<K> r;
+  const double ib = 1.0 / b.v;
+  r.v = a.v * ib;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) * ib;
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator-(const Dual<K>& a) {
+  Dual<K> r;
+  r.v = -a.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = -a.d[k];
+  return r;
+}
+
+// ---- Dual (op) double ---------------------------------------------------------
+template <int K>
+DDP_HD Dual<K> operator+(const Dual<K>& a, double b) {
+  Dual<K> r = a;
+  r.v += b;
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator+(double b, const Dual<K>& a) { return a + b; }
+template <int K>
+DDP_HD Dual<K> operator-(const Dual<K>& a, double b) {
+  Dual<K> r = a;
+  r.v -= b;
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator-(double b, const Dual<K>& a) {
+  Dual<K> r;
+  r.v = b - a.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = -a.d[k];
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator*(const Dual<K>& a, double b) {
+  Dual<K> r;
+  r.v = a.v * b;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = a.d[k] * b;
+  return r;
+}
+template <int K>
+DDP_HD Dual<K> operator*(double b, const Dual<K>& a) { return a * b; }
+template <int K>
+DDP_HD Dual<K> operator/(const Dual<K>& a, double b) { return a * (1.0 / b); }
+template <int K>
+DDP_HD Dual<K> operator/(double a, const Dual<K>& b) {
+  Dual<K> r;
+  const double ib = 1.0 / b.v;
+  r.v = a * ib;
+  const double s = -r.v * ib;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = s * b.d[k];
+  return r;
+}
+template <int K>
+DDP_HD Dual<K>& operator+=(Dual<K>& a, const Dual<K>& b) { a = a + b; return a; }
+template <int K>
+DDP_HD Dual<K>& operator-=(Dual<K>& a, const Dual<K>& b) { a = a - b; return a; }
+template <int K>
+DDP_HD Dual<K>& operator+=(Dual<K>& a, double b) { a.v += b; return a; }
+
+// ---- elementary functions -----------------------------------------------------
+DDP_HD void sincos_(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  ::sincos(a, s, c);
+#else
+  *s = ::sin(a);
+  *c = ::cos(a);
+#endif
+}
+template <int K>
+DDP_HD void sincos_(const Dual<K>& a, Dual<K>* s, Dual<K>* c) {
+  double sv, cv;
+  sincos_(a.v, &sv, &cv);
+  s->v = sv;
+  c->v = cv;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    s->d[k] = cv * a.d[k];
+    c->d[k] = -sv * a.d[k];
+  }
+}
+DDP_HD double sqrt_(double a) { return ::sqrt(a); }
+template <int K>
+DDP_HD Dual<K> sqrt_(const Dual<K>& a) {
+  Dual<K> r;
+  r.v = ::sqrt(a.v);
+  const double h = 0.5 / r.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = h * a.d[k];
+  return r;
+}
+
+}  // namespace ddp

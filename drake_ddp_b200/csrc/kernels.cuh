@@ -1,0 +1,744 @@
+// CUDA kernels of the batched iLQR hot path (sm_100a).  One template per reference
+// function; the reference line ranges each one replaces are cited at the kernel.
+//
+// Layouts (row-major fp64, trajectory-major, time-major tiles):
+//   x_bar [B][N][n]  u_bar [B][T][m]  kappa [B][T][m]  dV [B][T]
+//   K [B][T][m][n]   fx [B][T][n][n]  fu [B][T][n][m]
+//   candidates: xc [B][A][N][n]  uc [B][A][T][m]  Lc, Ec [B][A]
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "models.h"
+
+namespace ddp {
+
+struct Dev {
+  int n, m, N, T, B, A, n_eps, diag_cost;
+  double delta, gamma;
+  const double* params;
+  const double *Q, *R, *Qf, *x_nom, *x0, *eps_table;
+  double *x_bar, *u_bar, *K, *kappa, *dV, *fx, *fu;
+  double *xc, *uc, *Lc, *Ec;
+  double *L, *L_new, *eps, *improvement;
+  int *ls_iters, *status, *active, *resolved, *acc, *iters, *counters;
+  // keypoints
+  int kp_method, minN, maxN;
+  double jerk_thr, err_thr;
+  int *kplist, *kpcount, *seg_s, *seg_e;
+  unsigned char *flag, *done;
+  int *segs[2], *nseg[2], *evallist, *evalcount;
+};
+
+// Thread mapping per model size class.
+template <class Model>
+struct Cfg {
+  static constexpr int n = Model::n, m = Model::m;
+  static constexpr bool small = (n + m) <= 8;
+  static constexpr int G_ROLL = small ? 1 : 4;      // lanes per rollout candidate
+  static constexpr int G_LIN = small ? 1 : 16;      // lanes per linearization point
+  static constexpr int K_LIN = (n + m + G_LIN - 1) / G_LIN;  // seed directions per lane
+  static constexpr int BWD_THREADS = small ? 32 : 128;
+};
+
+__device__ __forceinline__ unsigned group_mask(int G) {
+  if (G >= 32) return 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  return ((1u << G) - 1u) << (lane / G * G);
+}
+
+// =============================================================================================
+// K1  closed-loop rollout + cost of line-search candidates.
+// Replaces the body of _linesearch (/root/reference/ilqr.py:306-327) and _calc_dynamics
+// (:208-231) for candidates eps_table[ls_base .. ls_base+A) of every unresolved trajectory.
+// G lanes cooperate on one candidate: feedback rows are split over the lanes, the dynamics
+// are evaluated redundantly by each lane (identical values, so control flow stays uniform).
+// =============================================================================================
+template <class Model, int G>
+__global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base) {
+  constexpr int n = Model::n, m = Model::m;
+  constexpr int RPL = (m + G - 1) / G;  // feedback rows per lane
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = gtid / G, lane = gtid % G;
+  if (item >= d.B * d.A) return;
+  const int b = item / d.A, ai = item % d.A;
+  if (!d.active[b] || d.resolved[b]) return;
+  const int c = ls_base + ai;
+  if (c >= d.n_eps) {
+    if (lane == 0) {
+      d.Lc[item] = nan("");
+      d.Ec[item] = 0.0;
+    }
+    return;
+  }
+  const unsigned mask = group_mask(G);
+  const int gbase = (threadIdx.x & 31) / G * G;
+  const double eps = d.eps_table[c];
+  const double ecoef = -eps * (1.0 - eps / 2.0);
+  const int N = d.N, T = d.T;
+  const double* xnom = d.x_nom + (size_t)b * n;
+  double* xo = d.xc + (size_t)item * N * n;
+  double* uo = d.uc + (size_t)item * T * m;
+
+  double x[n], xn[n], u[m];
+#pragma unroll
+  for (int j = 0; j < n; ++j) x[j] = d.x0[(size_t)b * n + j];
+#pragma unroll
+  for (int j = 0; j < n; ++j)
+    if (j % G == lane) xo[j] = x[j];
+
+  double L = 0.0, E = 0.0;
+  bool ok = true;
+  int t = 0;
+  for (; t < T; ++t) {
+    const double* Kt = d.K + ((size_t)b * T + t) * m * n;
+    const double* xb = d.x_bar + ((size_t)b * N + t) * n;
+    const double* ub = d.u_bar + ((size_t)b * T + t) * m;
+    const double* kp = d.kappa + ((size_t)b * T + t) * m;
+    // u_t = u_bar_t - eps*kappa_t - K_t (x_t - x_bar_t)            (ilqr.py:313)
+    double dx[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) dx[j] = x[j] - xb[j];
+    double mine[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const int r = lane + G * i;
+      double acc = 0.0;
+      if (r < m) {
+        const double* Kr = Kt + (size_t)r * n;
+#pragma unroll
+        for (int j = 0; j < n; ++j) acc = fma(Kr[j], dx[j], acc);
+        acc = ub[r] - eps * kp[r] - acc;
+      }
+      mine[i] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < m; ++r) {
+      if (G == 1) u[r] = mine[r];
+      else u[r] = __shfl_sync(mask, mine[r / G], gbase + (r % G));
+    }
+    // x_{t+1} = f(x_t, u_t)                                          (ilqr.py:316)
+    Model::template step<double>(x, u, xn, d.params);
+    bool fin = true;
+#pragma unroll
+    for (int j = 0; j < n; ++j) fin = fin && isfinite(xn[j]);
+    if (!fin) {  // the reference gets a RuntimeError from Drake: L = inf, stop   (:317-323)
+      ok = false;
+      break;
+    }
+    // running cost uses the pre-step state                         (ilqr.py:325)
+    if (d.diag_cost) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const double e = x[j] - xnom[j];
+        s = fma(d.Q[j * n + j] * e, e, s);
+      }
+#pragma unroll
+      for (int r = 0; r < m; ++r) s = fma(d.R[r * m + r] * u[r], u[r], s);
+      L += s;
+    } else {
+      double s = 0.0;
+#pragma unroll 1
+      for (int j = lane; j < n; j += G) {
+        double row = 0.0;
+        for (int k = 0; k < n; ++k) row = fma(d.Q[j * n + k], x[k] - xnom[k], row);
+        s = fma(x[j] - xnom[j], row, s);
+      }
+#pragma unroll 1
+      for (int r = lane; r < m; r += G) {
+        double row = 0.0;
+        for (int k = 0; k < m; ++k) row = fma(d.R[r * m + k], u[k], row);
+        s = fma(u[r], row, s);
+      }
+      L += s;
+    }
+    E += ecoef * d.dV[(size_t)b * T + t];                      //  (ilqr.py:326)
+#pragma unroll
+    for (int r = 0; r < m; ++r)
+      if (r % G == lane) uo[(size_t)t * m + r] = u[r];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      x[j] = xn[j];
+      if (j % G == lane) xo[(size_t)(t + 1) * n + j] = xn[j];
+    }
+  }
+  // terminal cost                                                   (ilqr.py:327)
+  if (ok) {
+    if (d.diag_cost) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const double e = x[j] - xnom[j];
+        s = fma(d.Qf[j * n + j] * e, e, s);
+      }
+      L += s;
+    } else {
+      double s = 0.0;
+#pragma unroll 1
+      for (int j = lane; j < n; j += G) {
+        double row = 0.0;
+        for (int k = 0; k < n; ++k) row = fma(d.Qf[j * n + k], x[k] - xnom[k], row);
+        s = fma(x[j] - xnom[j], row, s);
+      }
+      L += s;
+    }
+    if (!d.diag_cost && G > 1) {
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) L += __shfl_xor_sync(mask, L, o);
+    }
+  } else {
+    L = INFINITY;
+  }
+  if (lane == 0) {
+    d.Lc[item] = L;
+    d.Ec[item] = E;
+  }
+}
+
+// =============================================================================================
+// K2  first-satisfying pick (ilqr.py:329-337) over the A candidates of this round.
+// =============================================================================================
+__global__ void pick_kernel(Dev d, int ls_base) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  if (!d.active[b] || d.resolved[b]) return;
+  const double Llast = d.L[b];
+  for (int ai = 0; ai < d.A; ++ai) {
+    const int c = ls_base + ai;
+    if (c >= d.n_eps) break;
+    const double Lcand = d.Lc[(size_t)b * d.A + ai];
+    const double improvement = Llast - Lcand;
+    if (improvement > d.gamma * d.Ec[(size_t)b * d.A + ai]) {
+      d.acc[b] = ai;
+      d.resolved[b] = 1;
+      d.eps[b] = d.eps_table[c];
+      d.ls_iters[b] = c + 1;
+      d.L_new[b] = Lcand;
+      return;
+    }
+  }
+  d.acc[b] = -1;
+  if (ls_base + d.A >= d.n_eps) {  // eps < 1e-8: RuntimeError("linesearch failed ...")  (:337)
+    d.status[b] = 2;
+    d.active[b] = 0;
+    d.resolved[b] = 1;
+    d.ls_iters[b] = d.n_eps;
+  } else {
+    atomicAdd(&d.counters[0], 1);
+  }
+}
+
+// u_bar <- u, x_bar <- x of the accepted candidate (ilqr.py:375-376).
+__global__ void commit_kernel(Dev d) {
+  const int b = blockIdx.y;
+  if (!d.active[b]) return;
+  const int ai = d.acc[b];
+  if (ai < 0) return;
+  const size_t nx = (size_t)d.N * d.n, nu = (size_t)d.T * d.m;
+  const double* xs = d.xc + ((size_t)b * d.A + ai) * nx;
+  const double* us = d.uc + ((size_t)b * d.A + ai) * nu;
+  double* xd = d.x_bar + (size_t)b * nx;
+  double* ud = d.u_bar + (size_t)b * nu;
+  for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nx + nu; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nx) xd[i] = xs[i];
+    else ud[i - nx] = us[i - nx];
+  }
+}
+// mark the commit of trajectory b as consumed
+__global__ void commit_done_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < d.B) d.acc[b] = -1;
+}
+
+// reset per-iteration line-search state
+__global__ void begin_iter_kernel(Dev d, int force_all) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) {
+    d.counters[0] = 0;
+    d.counters[1] = 0;
+  }
+  if (b >= d.B) return;
+  if (force_all) {
+    d.active[b] = 1;
+  }
+  d.resolved[b] = 0;
+  d.acc[b] = -1;
+}
+
+// improvement = L - L_new; L = L_new; stop when improvement <= delta (ilqr.py:692,706-708)
+__global__ void finish_iter_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  if (!d.active[b]) return;
+  const double imp = d.L[b] - d.L_new[b];
+  d.improvement[b] = imp;
+  d.L[b] = d.L_new[b];
+  d.iters[b] += 1;
+  if (imp > d.delta) {
+    atomicAdd(&d.counters[1], 1);
+  } else {
+    d.active[b] = 0;
+    d.status[b] = 1;
+  }
+}
+
+// =============================================================================================
+// K3  keypoint selection (ilqr.py:417-539) -> ascending list per trajectory.
+// =============================================================================================
+// get_keypoints_set_interval, ilqr.py:417-432
+__global__ void kp_set_interval_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  int* list = d.kplist + (size_t)b * d.T;
+  int cnt = 0;
+  for (int t = 0; t < d.N - 1; t += d.minN) list[cnt++] = t;
+  if (list[cnt - 1] != d.N - 2) list[cnt - 1] = d.N - 2;
+  d.kpcount[b] = cnt;
+}
+// calc_jerk_profile + threshold test, ilqr.py:470-486,454-455: flag[b][t] = any_i jerk[t,i] > thr
+__global__ void jerk_flag_kernel(Dev d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= d.N - 3 || !d.active[b]) return;
+  const int n = d.n, dof = n / 2;
+  const double* x = d.x_bar + ((size_t)b * d.N + t) * n + dof;
+  bool any = false;
+  for (int i = 0; i < dof; ++i) {
+    const double a1 = x[2 * n + i] - x[n + i];
+    const double a2 = x[n + i] - x[i];
+    any = any || ((a1 - a2) > d.jerk_thr);
+  }
+  d.flag[(size_t)b * d.N + t] = any ? 1 : 0;
+}
+// get_keypoints_adaptive_jerk counter scan, ilqr.py:447-466
+__global__ void jerk_scan_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  int* list = d.kplist + (size_t)b * d.T;
+  const unsigned char* flag = d.flag + (size_t)b * d.N;
+  int cnt = 0, counter = 0;
+  list[cnt++] = 0;
+  for (int t = 0; t < d.N - 3; ++t) {
+    counter += 1;
+    if (counter >= d.minN && flag[t]) {
+      if (cnt < d.T) list[cnt++] = t;
+      counter = 0;
+    }
+    if (counter >= d.maxN) {
+      if (cnt < d.T) list[cnt++] = t;
+      counter = 0;
+    }
+  }
+  if (list[cnt - 1] != d.N - 2) list[cnt - 1] = d.N - 2;
+  d.kpcount[b] = cnt;
+}
+// segment lookup for the interpolation: t in [kp_i, kp_{i+1}) -> (kp_i, kp_{i+1}); else -1
+__global__ void segments_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  const int* list = d.kplist + (size_t)b * d.T;
+  int* ss = d.seg_s + (size_t)b * d.T;
+  int* se = d.seg_e + (size_t)b * d.T;
+  const int cnt = d.kpcount[b];
+  for (int t = 0; t < d.T; ++t) ss[t] = -1;
+  for (int i = 0; i + 1 < cnt; ++i)
+    for (int t = list[i]; t < list[i + 1]; ++t) {
+      ss[t] = list[i];
+      se[t] = list[i + 1];
+    }
+}
+
+// ---- iterativeError (ilqr.py:488-593), level-synchronous ---------------------------------
+__global__ void ie_init_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  for (int t = 0; t < d.N; ++t) d.done[(size_t)b * d.N + t] = 0;
+  d.segs[0][(size_t)b * 2 * d.T + 0] = 0;
+  d.segs[0][(size_t)b * 2 * d.T + 1] = d.N - 2;
+  d.nseg[0][b] = 1;
+  d.nseg[1][b] = 0;
+}
+// collect the indices whose Jacobian this level needs (start/mid/end of every segment longer
+// than minN), ilqr.py:557-577
+__global__ void ie_collect_kernel(Dev d, int cur) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  const int ns = d.nseg[cur][b];
+  const int* segs = d.segs[cur] + (size_t)b * 2 * d.T;
+  int* ev = d.evallist + (size_t)b * d.T;
+  unsigned char* done = d.done + (size_t)b * d.N;
+  int ne = 0;
+  for (int i = 0; i < ns; ++i) {
+    const int s = segs[2 * i], e = segs[2 * i + 1];
+    if (e - s <= d.minN) continue;
+    const int idx[3] = {s, (s + e) / 2, e};
+    for (int k = 0; k < 3; ++k)
+      if (!done[idx[k]]) {
+        done[idx[k]] = 1;
+        ev[ne++] = idx[k];
+      }
+  }
+  d.evalcount[b] = ne;
+}
+// check_one_matrix_error (ilqr.py:579-591) for every segment of the level; split the bad ones
+// (ilqr.py:517-521).  One block per trajectory.
+__global__ void ie_check_kernel(Dev d, int cur) {
+  const int b = blockIdx.x;
+  if (!d.active[b]) return;
+  const int n = d.n, nn = n * n;
+  const int ns = d.nseg[cur][b];
+  const int* segs = d.segs[cur] + (size_t)b * 2 * d.T;
+  int* out = d.segs[cur ^ 1] + (size_t)b * 2 * d.T;
+  __shared__ double red[32];
+  __shared__ int nout;
+  if (threadIdx.x == 0) nout = 0;
+  __syncthreads();
+  for (int i = 0; i < ns; ++i) {
+    const int s = segs[2 * i], e = segs[2 * i + 1];
+    if (e - s <= d.minN) continue;
+    const int mid = (s + e) / 2;
+    const double* fs = d.fx + ((size_t)b * d.T + s) * nn;
+    const double* fm = d.fx + ((size_t)b * d.T + mid) * nn;
+    const double* fe = d.fx + ((size_t)b * d.T + e) * nn;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < nn; k += blockDim.x) {
+      const double lin = (fe[k] + fs[k]) / 2.0;
+      const double df = lin - fm[k];
+      acc += df * df;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (blockDim.x + 31) / 32; ++w) tot += red[w];
+      if (tot / (2.0 * n) > d.err_thr) {
+        out[2 * nout] = s;
+        out[2 * nout + 1] = mid;
+        out[2 * nout + 2] = mid;
+        out[2 * nout + 3] = e;
+        nout += 2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    d.nseg[cur ^ 1][b] = nout;
+    d.nseg[cur][b] = 0;
+  }
+}
+// keypoints = every index whose Jacobian was evaluated, ascending (ilqr.py:535-537)
+__global__ void ie_finish_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  int* list = d.kplist + (size_t)b * d.T;
+  int cnt = 0;
+  for (int t = 0; t < d.N - 1; ++t)
+    if (d.done[(size_t)b * d.N + t]) list[cnt++] = t;
+  d.kpcount[b] = cnt;
+  d.evalcount[b] = 0;
+}
+
+// =============================================================================================
+// K4  dynamics linearization at listed timesteps (replaces _calc_dynamics_partials,
+// ilqr.py:233-272, and the keypoint loop :409-411).  Forward-mode AD with the n+m seed
+// directions spread over the G lanes of a group (K per lane); lane L owns directions
+// g = k*G + L so that stores of one Jacobian row are contiguous across lanes.
+// =============================================================================================
+template <class Model, int G, int K>
+__global__ void __launch_bounds__(128) linearize_kernel(Dev d, const int* list, const int* count) {
+  constexpr int n = Model::n, m = Model::m;
+  typedef Dual<K> D;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t item = gtid / G;
+  const int lane = (int)(gtid % G);
+  if (item >= (size_t)d.B * d.T) return;
+  const int b = (int)(item / d.T), i = (int)(item % d.T);
+  if (!d.active[b] || i >= count[b]) return;
+  const int t = list[(size_t)b * d.T + i];
+  const double* xp = d.x_bar + ((size_t)b * d.N + t) * n;
+  const double* up = d.u_bar + ((size_t)b * d.T + t) * m;
+  D xs[n], us[m], out[n];
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    xs[j].v = xp[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xs[j].d[k] = (k * G + lane == j) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < m; ++j) {
+    us[j].v = up[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) us[j].d[k] = (k * G + lane == n + j) ? 1.0 : 0.0;
+  }
+  Model::template step<D>(xs, us, out, d.params);
+  double* fx = d.fx + ((size_t)b * d.T + t) * n * n;
+  double* fu = d.fu + ((size_t)b * d.T + t) * n * m;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int g = k * G + lane;
+    if (g < n) {
+#pragma unroll
+      for (int r = 0; r < n; ++r) fx[r * n + g] = out[r].d[k];
+    } else if (g < n + m) {
+#pragma unroll
+      for (int r = 0; r < n; ++r) fu[r * m + (g - n)] = out[r].d[k];
+    }
+  }
+}
+
+// =============================================================================================
+// K5  interpolate_derivatives (ilqr.py:596-621): fx_j = fx_s + (fx_e - fx_s)*(j-s)/(e-s)
+// =============================================================================================
+__global__ void interp_kernel(Dev d) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  if (!d.active[b]) return;
+  const int s = d.seg_s[(size_t)b * d.T + t];
+  if (s < 0 || s == t) return;
+  const int e = d.seg_e[(size_t)b * d.T + t];
+  const double w = (double)(t - s), den = (double)(e - s);
+  const int nn = d.n * d.n, nm = d.n * d.m;
+  const double* fs = d.fx + ((size_t)b * d.T + s) * nn;
+  const double* fe = d.fx + ((size_t)b * d.T + e) * nn;
+  double* ft = d.fx + ((size_t)b * d.T + t) * nn;
+  for (int k = threadIdx.x; k < nn; k += blockDim.x) ft[k] = fs[k] + (fe[k] - fs[k]) * w / den;
+  const double* us = d.fu + ((size_t)b * d.T + s) * nm;
+  const double* ue = d.fu + ((size_t)b * d.T + e) * nm;
+  double* ut = d.fu + ((size_t)b * d.T + t) * nm;
+  for (int k = threadIdx.x; k < nm; k += blockDim.x) ut[k] = us[k] + (ue[k] - us[k]) * w / den;
+}
+
+// =============================================================================================
+// K6  backward Riccati sweep (replaces _backward_pass, ilqr.py:623-667, with the cost
+// partials of :161-206).  One CTA per trajectory; Vxx, Vx and the per-step tiles live in
+// shared memory; sequential over t = N-2 .. 0.
+// =============================================================================================
+template <int n, int m>
+struct BwdSmem {
+  double Vxx[n * n], W[n * n], Fx[n * n];
+  double Fu[n * m], Wu[n * m], Qux[m * n], Kt[m * n];
+  double Quu[m * m], Inv[m * m];
+  double Vx[n], Qx[n], xb[n];
+  double Qu[m], g[m], kap[m], ub[m];
+};
+
+// explicit inverse of the m x m matrix A (destroyed) into Inv by Gauss-Jordan with partial
+// pivoting; one warp, lane r owns row r.  Stands in for np.linalg.inv(Quu) (ilqr.py:655).
+template <int m>
+__device__ void invert_warp(double* A, double* Inv) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < m * m; i += 32) Inv[i] = (i / m == i % m) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int c = 0; c < m; ++c) {
+    // pivot search over rows >= c
+    double best = (lane >= c && lane < m) ? fabs(A[lane * m + c]) : -1.0;
+    int arg = lane;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (arg != c) {
+      for (int j = lane; j < m; j += 32) {
+        double tmp = A[c * m + j];
+        A[c * m + j] = A[arg * m + j];
+        A[arg * m + j] = tmp;
+        tmp = Inv[c * m + j];
+        Inv[c * m + j] = Inv[arg * m + j];
+        Inv[arg * m + j] = tmp;
+      }
+    }
+    __syncwarp();
+    const double piv = 1.0 / A[c * m + c];
+    __syncwarp();
+    for (int j = lane; j < m; j += 32) {
+      A[c * m + j] *= piv;
+      Inv[c * m + j] *= piv;
+    }
+    __syncwarp();
+    if (lane < m && lane != c) {
+      const double f = A[lane * m + c];
+      for (int j = 0; j < m; ++j) {
+        A[lane * m + j] = fma(-f, A[c * m + j], A[lane * m + j]);
+        Inv[lane * m + j] = fma(-f, Inv[c * m + j], Inv[lane * m + j]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class Model, int NT>
+__global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
+  constexpr int n = Model::n, m = Model::m;
+  const int b = blockIdx.x;
+  if (!d.active[b]) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem<n, m>& s = *reinterpret_cast<BwdSmem<n, m>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int N = d.N, T = d.T;
+  const double* Q = d.Q;
+  const double* R = d.R;
+  const double* Qf = d.Qf;
+  const double* xnom = d.x_nom + (size_t)b * n;
+
+  // Vx, Vxx <- terminal cost partials at x_bar[:, -1]            (ilqr.py:638, 203-204)
+  {
+    const double* xl = d.x_bar + ((size_t)b * N + (N - 1)) * n;
+    for (int i = tid; i < n * n; i += NT) s.Vxx[i] = 2.0 * Qf[i];
+    for (int i = tid; i < n; i += NT) {
+      double a = 0.0, c = 0.0;
+      for (int j = 0; j < n; ++j) {
+        a = fma(2.0 * Qf[i * n + j], xl[j], a);
+        c = fma(2.0 * xnom[j], Qf[j * n + i], c);
+      }
+      s.Vx[i] = a - c;
+    }
+  }
+  __syncthreads();
+
+  for (int t = T - 1; t >= 0; --t) {
+    const double* gfx = d.fx + ((size_t)b * T + t) * n * n;
+    const double* gfu = d.fu + ((size_t)b * T + t) * n * m;
+    for (int i = tid; i < n * n; i += NT) s.Fx[i] = gfx[i];
+    for (int i = tid; i < n * m; i += NT) s.Fu[i] = gfu[i];
+    for (int i = tid; i < n; i += NT) s.xb[i] = d.x_bar[((size_t)b * N + t) * n + i];
+    for (int i = tid; i < m; i += NT) s.ub[i] = d.u_bar[((size_t)b * T + t) * m + i];
+    __syncthreads();
+    // W = Vxx fx, Wu = Vxx fu
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int i = idx / n, k = idx % n;
+      double a = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) a = fma(s.Vxx[i * n + j], s.Fx[j * n + k], a);
+      s.W[idx] = a;
+    }
+    for (int idx = tid; idx < n * m; idx += NT) {
+      const int i = idx / m, r = idx % m;
+      double a = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) a = fma(s.Vxx[i * n + j], s.Fu[j * m + r], a);
+      s.Wu[idx] = a;
+    }
+    // Qx = lx + fx' Vx ; Qu = lu + fu' Vx                         (ilqr.py:651-652,180-181)
+    for (int k = tid; k < n; k += NT) {
+      double a = 0.0, c = 0.0;
+      if (d.diag_cost) {
+        a = 2.0 * Q[k * n + k] * s.xb[k];
+        c = 2.0 * xnom[k] * Q[k * n + k];
+      } else {
+        for (int j = 0; j < n; ++j) {
+          a = fma(2.0 * Q[k * n + j], s.xb[j], a);
+          c = fma(2.0 * xnom[j], Q[j * n + k], c);
+        }
+      }
+      double q = a - c;
+      for (int i = 0; i < n; ++i) q = fma(s.Fx[i * n + k], s.Vx[i], q);
+      s.Qx[k] = q;
+    }
+    for (int r = tid; r < m; r += NT) {
+      double a = 0.0;
+      for (int j = 0; j < m; ++j) a = fma(2.0 * R[r * m + j], s.ub[j], a);
+      for (int i = 0; i < n; ++i) a = fma(s.Fu[i * m + r], s.Vx[i], a);
+      s.Qu[r] = a;
+    }
+    __syncthreads();
+    // Qxx = lxx + fx' W (into Vxx) ; Qux = fu' W ; Quu = luu + fu' Wu   (ilqr.py:653-656)
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int k = idx / n, l = idx % n;
+      double a = 2.0 * Q[idx];
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) a = fma(s.Fx[i * n + k], s.W[i * n + l], a);
+      s.Vxx[idx] = a;
+    }
+    for (int idx = tid; idx < m * n; idx += NT) {
+      const int r = idx / n, l = idx % n;
+      double a = 0.0;
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) a = fma(s.Fu[i * m + r], s.W[i * n + l], a);
+      s.Qux[idx] = a;
+    }
+    for (int idx = tid; idx < m * m; idx += NT) {
+      const int r = idx / m, q = idx % m;
+      double a = 2.0 * R[idx];
+      for (int i = 0; i < n; ++i) a = fma(s.Fu[i * m + r], s.Wu[i * m + q], a);
+      s.Quu[idx] = a;
+    }
+    __syncthreads();
+    if (tid < 32) invert_warp<m>(s.Quu, s.Inv);                 // ilqr.py:655
+    __syncthreads();
+    // kappa = Quu^-1 Qu ; K = Quu^-1 Qux ; g = Qu' Quu^-1          (ilqr.py:659-663)
+    for (int r = tid; r < m; r += NT) {
+      double a = 0.0, c = 0.0;
+      for (int j = 0; j < m; ++j) {
+        a = fma(s.Inv[r * m + j], s.Qu[j], a);
+        c = fma(s.Qu[j], s.Inv[j * m + r], c);
+      }
+      s.kap[r] = a;
+      s.g[r] = c;
+    }
+    for (int idx = tid; idx < m * n; idx += NT) {
+      const int r = idx / n, l = idx % n;
+      double a = 0.0;
+      for (int j = 0; j < m; ++j) a = fma(s.Inv[r * m + j], s.Qux[j * n + l], a);
+      s.Kt[idx] = a;
+    }
+    __syncthreads();
+    // outputs + value update                                       (ilqr.py:659-667)
+    double* gK = d.K + ((size_t)b * T + t) * m * n;
+    for (int idx = tid; idx < m * n; idx += NT) gK[idx] = s.Kt[idx];
+    for (int r = tid; r < m; r += NT) d.kappa[((size_t)b * T + t) * m + r] = s.kap[r];
+    if (tid == 0) {
+      double a = 0.0;
+      for (int j = 0; j < m; ++j) a = fma(s.g[j], s.Qu[j], a);
+      d.dV[(size_t)b * T + t] = a;
+    }
+    for (int k = tid; k < n; k += NT) {
+      double a = 0.0;
+      for (int j = 0; j < m; ++j) a = fma(s.g[j], s.Qux[j * n + k], a);
+      s.Vx[k] = s.Qx[k] - a;
+    }
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int k = idx / n, l = idx % n;
+      double a = 0.0;
+      for (int j = 0; j < m; ++j) a = fma(s.Qux[j * n + k], s.Kt[j * n + l], a);
+      s.Vxx[idx] -= a;
+    }
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
+// fp64 pipe microbenchmarks (bench.py states the fp64 roofline next to the HBM one)
+// =============================================================================================
+__global__ void peak_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void peak_dmma_kernel(double* out, int iters) {
+  double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+  double a = threadIdx.x * 1e-3, b = 0.5;
+  for (int i = 0; i < iters; ++i) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0[0]), "+d"(c0[1]) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c1[0]), "+d"(c1[1]) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c2[0]), "+d"(c2[1]) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c3[0]), "+d"(c3[1]) : "d"(a), "d"(b));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+}
+
+}  // namespace ddp

@@ -1,0 +1,457 @@
+// Fixed analytic discrete-time models x+ = f(x, u), shared by the CUDA kernels
+// (device) and by the host model library the CPU oracle's dynamics shim calls.
+//
+// They stand in for the Drake MultibodyPlant discrete update the reference
+// calls at /root/reference/ilqr.py:223-229 (forward) and :259-268 (AutoDiff).
+// Drake is not available offline, so these are this repo's own models: same
+// state sizes and physical constants as the reference's example scripts, a
+// semi-implicit Euler discrete map (v+ = v + h a(q,v,u); q+ = q + h N(q) v+),
+// and closed-form compliant contact (pressure field p = E(1 - r/R) integrated
+// over the sphere/plane contact disk).  See DESIGN.md "Models".
+//
+// Every model is   template <class S> static void step(x, u, xn, p)
+// with S = double (rollouts) or S = ddp::Dual<K> (linearization).
+#pragma once
+#include "dual.h"
+
+namespace ddp {
+
+enum ModelId {
+  MODEL_PENDULUM = 0,       // n=2  m=1   pendulum.py
+  MODEL_ACROBOT = 1,        // n=4  m=1   acrobot.py
+  MODEL_CARTPOLE = 2,       // n=4  m=1   cart_pole.py
+  MODEL_CARTPOLE_WALL = 3,  // n=4  m=1   cart_pole_with_wall.py
+  MODEL_QUADRUPED = 4,      // n=36 m=12  mini_cheetah-scale (Euler-angle base)
+  MODEL_ARM_BALL = 5,       // n=27 m=7   kinova/panda-scale arm pushing a ball
+  MODEL_AFFINE_SIN_4_1 = 10,   // x+ = A x + B u + 0.01 sin x (test stub, any A,B)
+  MODEL_AFFINE_SIN_6_2 = 11,
+  MODEL_AFFINE_SIN_27_7 = 12,
+  MODEL_AFFINE_SIN_36_12 = 13,
+  MODEL_AFFINE_SIN_37_12 = 14,
+};
+
+// ------------------------------------------------------------------------------
+// Pendulum.  x = [theta, thetadot], theta = 0 hanging down.
+// p = [dt, mass, length, damping, g]
+struct Pendulum {
+  static constexpr int n = 2, m = 1, np = 5;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    const double h = p[0], ml2 = p[1] * p[2] * p[2], mgl = p[1] * p[4] * p[2];
+    S s, c;
+    sincos_(x[0], &s, &c);
+    S a = (u[0] - p[3] * x[1] - mgl * s) / ml2;
+    S v1 = x[1] + h * a;
+    xn[0] = x[0] + h * v1;
+    xn[1] = v1;
+  }
+};
+
+// ------------------------------------------------------------------------------
+// Acrobot (elbow actuated).  x = [q1, q2, q1dot, q2dot].
+// p = [dt, m1, m2, l1, lc1, lc2, Ic1, Ic2, b1, b2, g]
+struct Acrobot {
+  static constexpr int n = 4, m = 1, np = 11;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    const double h = p[0], m1 = p[1], m2 = p[2], l1 = p[3], lc1 = p[4], lc2 = p[5];
+    const double I1 = p[6] + m1 * lc1 * lc1, I2 = p[7] + m2 * lc2 * lc2;
+    const double b1 = p[8], b2 = p[9], g = p[10];
+    const double k = m2 * l1 * lc2;
+    S s1, c1, s2, c2, s12, c12;
+    sincos_(x[0], &s1, &c1);
+    sincos_(x[1], &s2, &c2);
+    sincos_(x[0] + x[1], &s12, &c12);
+    (void)c1;
+    (void)c12;
+    S M11 = (I1 + I2 + m2 * l1 * l1) + (2.0 * k) * c2;
+    S M12 = I2 + k * c2;
+    const double M22 = I2;
+    // M qdd = tau_g + B u - C qd - b qd
+    S hq = k * s2;
+    S r1 = hq * x[3] * (2.0 * x[2] + x[3]) - (m1 * g * lc1 + m2 * g * l1) * s1 -
+           (m2 * g * lc2) * s12 - b1 * x[2];
+    S r2 = u[0] - hq * x[2] * x[2] - (m2 * g * lc2) * s12 - b2 * x[3];
+    S det = M11 * M22 - M12 * M12;
+    S a1 = (M22 * r1 - M12 * r2) / det;
+    S a2 = (M11 * r2 - M12 * r1) / det;
+    S v1 = x[2] + h * a1, v2 = x[3] + h * a2;
+    xn[0] = x[0] + h * v1;
+    xn[1] = x[1] + h * v2;
+    xn[2] = v1;
+    xn[3] = v2;
+  }
+};
+
+// ------------------------------------------------------------------------------
+// Cart-pole, optionally with a compliant ball on the pole tip hitting a rigid
+// wall.  x = [cart x, theta, xdot, thetadot], theta = 0 hanging, pi upright.
+// p = [dt, mc, mp, l, g, ball_radius, modulus E, wall_face_x, substeps]
+template <bool WALL>
+struct CartPoleT {
+  static constexpr int n = 4, m = 1, np = 9;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    const double mc = p[1], mp = p[2], l = p[3], g = p[4];
+    const int sub = WALL ? (int)p[8] : 1;
+    const double h = p[0] / sub;
+    S q0 = x[0], q1 = x[1], v0 = x[2], v1 = x[3];
+    for (int it = 0; it < sub; ++it) {
+      S s, c;
+      sincos_(q1, &s, &c);
+      S r0 = u[0] + (mp * l) * v1 * v1 * s;
+      S r1 = -(mp * g * l) * s;
+      if (WALL) {
+        // tip ball: centre at x + l sin(theta); wall occupies x <= wall_face_x.
+        const double R = p[5], E = p[6], xw = p[7];
+        S depth = (xw + R) - (q0 + l * s);
+        if (val(depth) > 0.0) {
+          S F;
+          if (val(depth) < R) {
+            F = (3.14159265358979323846 * E) * depth * depth * (1.0 - depth * (2.0 / (3.0 * R)));
+          } else {
+            F = S((3.14159265358979323846 * E) * R * R / 3.0) + 0.0 * depth;
+          }
+          r0 = r0 + F;
+          r1 = r1 + F * (l * c);
+        }
+      }
+      const double M00 = mc + mp, M11 = mp * l * l;
+      S M01 = (mp * l) * c;
+      S det = M00 * M11 - M01 * M01;
+      S a0 = (M11 * r0 - M01 * r1) / det;
+      S a1 = (M00 * r1 - M01 * r0) / det;
+      v0 = v0 + h * a0;
+      v1 = v1 + h * a1;
+      q0 = q0 + h * v0;
+      q1 = q1 + h * v1;
+    }
+    xn[0] = q0;
+    xn[1] = q1;
+    xn[2] = v0;
+    xn[3] = v1;
+  }
+};
+typedef CartPoleT<false> CartPole;
+typedef CartPoleT<true> CartPoleWall;
+
+// ------------------------------------------------------------------------------
+// Compliant sphere / rigid plane normal force, depth >= 0, saturating at R.
+template <class S>
+DDP_HD S sphere_plane_force(const S& depth, double R, double E) {
+  const double piE = 3.14159265358979323846 * E;
+  if (val(depth) <= 0.0) return 0.0 * depth;
+  if (val(depth) >= R) return S(piE * R * R / 3.0) + 0.0 * depth;
+  return piE * depth * depth * (1.0 - depth * (2.0 / (3.0 * R)));
+}
+
+// ------------------------------------------------------------------------------
+// Quadruped, mini_cheetah scale: one rigid body (all link masses lumped) on four
+// 3-joint legs whose joint dynamics are rotor-inertia dominated; spherical feet
+// on compliant ground with regularised Coulomb friction.
+//   q = [px py pz | roll pitch yaw | (abad hip knee) x {FR, FL, HR, HL}]   (18)
+//   v = [world linear velocity | body angular velocity | joint rates]        (18)
+// p = [dt, substeps, mass, Ixx, Iyy, Izz, Ij_abad, Ij_hip, Ij_knee, joint_damping,
+//      l_abad, l_thigh, l_shank, hip_x, hip_y, foot_radius, E, mu, v_stiction, g]
+struct Quadruped {
+  static constexpr int n = 36, m = 12, np = 20;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    const int sub = (int)p[1];
+    const double h = p[0] / sub;
+    const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5];
+    const double bj = p[9], l1 = p[10], l2 = p[11], l3 = p[12];
+    const double hx = p[13], hy = p[14], rf = p[15], E = p[16], mu = p[17], vs = p[18];
+    const double g = p[19];
+    S q[18], v[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      q[i] = x[i];
+      v[i] = x[18 + i];
+    }
+    for (int it = 0; it < sub; ++it) {
+      S sr, cr, sp, cp, sy, cy;
+      sincos_(q[3], &sr, &cr);
+      sincos_(q[4], &sp, &cp);
+      sincos_(q[5], &sy, &cy);
+      // R = Rz(yaw) Ry(pitch) Rx(roll), body -> world
+      S R00 = cy * cp, R01 = cy * sp * sr - sy * cr, R02 = cy * sp * cr + sy * sr;
+      S R10 = sy * cp, R11 = sy * sp * sr + cy * cr, R12 = sy * sp * cr - cy * sr;
+      S R20 = -sp, R21 = cp * sr, R22 = cp * cr;
+      S Fx = 0.0 * q[0], Fy = Fx, Fz = Fx;  // world force on the body
+      S Tx = Fx, Ty = Fx, Tz = Fx;          // body-frame torque on the body
+      S acc[18];
+#pragma unroll
+      for (int leg = 0; leg < 4; ++leg) {
+        const double sx = (leg < 2) ? 1.0 : -1.0;
+        const double sd = (leg & 1) ? 1.0 : -1.0;
+        const S* ql = q + 6 + 3 * leg;
+        const S* vl = v + 6 + 3 * leg;
+        S sa, ca, sh, ch, sk, ck;
+        sincos_(ql[0], &sa, &ca);
+        sincos_(ql[1], &sh, &ch);
+        sincos_(ql[1] + ql[2], &sk, &ck);
+        const double ly = sd * l1;
+        S lx = -(l2 * sh) - l3 * sk;
+        S lz = -(l2 * ch) - l3 * ck;
+        // foot in body frame and its joint Jacobian (columns: abad, hip, knee)
+        S rx = hx * sx + lx;
+        S ry = hy * sd + (ly * ca - lz * sa);
+        S rz = ly * sa + lz * ca;
+        S J01 = lz, J02 = -(l3 * ck);
+        S J10 = -(ly * sa) - lz * ca, J11 = lx * sa, J12 = -(l3 * sk) * sa;
+        S J20 = ly * ca - lz * sa, J21 = -(lx * ca), J22 = (l3 * sk) * ca;
+        // foot height and world velocity
+        S cz = q[2] + R20 * rx + R21 * ry + R22 * rz;
+        S depth = rf - cz;
+        S tau0 = 0.0 * depth, tau1 = tau0, tau2 = tau0;
+        if (val(depth) > 0.0) {
+          // body-frame foot velocity relative to body origin: w x r + J qd
+          S bx = v[4] * rz - v[5] * ry + J01 * vl[1] + J02 * vl[2];
+          S by = v[5] * rx - v[3] * rz + J10 * vl[0] + J11 * vl[1] + J12 * vl[2];
+          S bz = v[3] * ry - v[4] * rx + J20 * vl[0] + J21 * vl[1] + J22 * vl[2];
+          S wx = v[0] + R00 * bx + R01 * by + R02 * bz;
+          S wy = v[1] + R10 * bx + R11 * by + R12 * bz;
+          S Fn = sphere_plane_force(depth, rf, E);
+          S sl = sqrt_(wx * wx + wy * wy + vs * vs);
+          S ftx = -(mu * Fn) * wx / sl;
+          S fty = -(mu * Fn) * wy / sl;
+          Fx = Fx + ftx;
+          Fy = Fy + fty;
+          Fz = Fz + Fn;
+          // force in body frame
+          S fbx = R00 * ftx + R10 * fty + R20 * Fn;
+          S fby = R01 * ftx + R11 * fty + R21 * Fn;
+          S fbz = R02 * ftx + R12 * fty + R22 * Fn;
+          Tx = Tx + (ry * fbz - rz * fby);
+          Ty = Ty + (rz * fbx - rx * fbz);
+          Tz = Tz + (rx * fby - ry * fbx);
+          tau0 = J10 * fby + J20 * fbz;
+          tau1 = J01 * fbx + J11 * fby + J21 * fbz;
+          tau2 = J02 * fbx + J12 * fby + J22 * fbz;
+        }
+        acc[6 + 3 * leg + 0] = (u[3 * leg + 0] + tau0 - bj * vl[0]) / p[6];
+        acc[6 + 3 * leg + 1] = (u[3 * leg + 1] + tau1 - bj * vl[1]) / p[7];
+        acc[6 + 3 * leg + 2] = (u[3 * leg + 2] + tau2 - bj * vl[2]) / p[8];
+      }
+      acc[0] = Fx / mass;
+      acc[1] = Fy / mass;
+      acc[2] = Fz / mass - g;
+      acc[3] = (Tx - (Iz - Iy) * v[4] * v[5]) / Ix;
+      acc[4] = (Ty - (Ix - Iz) * v[5] * v[3]) / Iy;
+      acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) / Iz;
+#pragma unroll
+      for (int i = 0; i < 18; ++i) v[i] = v[i] + h * acc[i];
+      // q+ = q + h N(q) v+   (ZYX Euler rates from body angular velocity)
+      q[0] = q[0] + h * v[0];
+      q[1] = q[1] + h * v[1];
+      q[2] = q[2] + h * v[2];
+      S tp = sp / cp;
+      S wyz = sr * v[4] + cr * v[5];
+      q[3] = q[3] + h * (v[3] + tp * wyz);
+      q[4] = q[4] + h * (cr * v[4] - sr * v[5]);
+      q[5] = q[5] + h * (wyz / cp);
+#pragma unroll
+      for (int i = 6; i < 18; ++i) q[i] = q[i] + h * v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      xn[i] = q[i];
+      xn[18 + i] = v[i];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------
+// Arm pushing a ball on a table, kinova_gen3 / panda_fr3 scale (7 + 7 + 13):
+//   q = [7 joint angles | ball quaternion (w x y z) | ball position]   (14)
+//   v = [7 joint rates  | ball angular velocity (world) | ball linear velocity] (13)
+// The arm is a 7R chain (alternating z / y joint axes, link lengths d[0..6]) whose
+// joint dynamics are rotor-inertia dominated with gravity compensated; a compliant
+// sphere at the tool tip pushes a free ball (sphere/sphere contact) that rests on a
+// compliant table (sphere/plane contact) with regularised friction at both contacts.
+// p = [dt, substeps, Ij, joint_damping, d0..d6 (7), tip_radius, ball_radius, ball_mass,
+//      E, mu, v_stiction, g, base_z]
+struct ArmBall {
+  static constexpr int n = 27, m = 7, np = 19;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    const int sub = (int)p[1];
+    const double h = p[0] / sub;
+    const double Ij = p[2], bj = p[3];
+    const double* d = p + 4;
+    const double rt = p[11], rb = p[12], mb = p[13], E = p[14], mu = p[15], vs = p[16];
+    const double g = p[17], bz = p[18];
+    const double Ib = 0.4 * mb * rb * rb;
+    S q[14], v[13];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) q[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) v[i] = x[14 + i];
+    for (int it = 0; it < sub; ++it) {
+      // ---- forward kinematics of the tool tip with its position Jacobian ----
+      // frame i: rotate about axis a_i (z for even i, y for odd i), then go d_i along
+      // the rotated local z.  Keep rotation columns and accumulate joint origins.
+      S Rxx = 1.0 + 0.0 * q[0], Rxy = 0.0 * q[0], Rxz = Rxy;
+      S Ryx = Rxy, Ryy = Rxx, Ryz = Rxy;
+      S Rzx = Rxy, Rzy = Rxy, Rzz = Rxx;
+      S ox[7], oy[7], oz[7], ax[7], ay[7], az[7];
+      S px = Rxy, py = Rxy, pz = Rxy + bz;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        S s, c;
+        sincos_(q[i], &s, &c);
+        ox[i] = px;
+        oy[i] = py;
+        oz[i] = pz;
+        if ((i & 1) == 0) {  // about local z
+          ax[i] = Rxz; ay[i] = Ryz; az[i] = Rzz;
+          S nxx = Rxx * c + Rxy * s, nxy = Rxy * c - Rxx * s;
+          S nyx = Ryx * c + Ryy * s, nyy = Ryy * c - Ryx * s;
+          S nzx = Rzx * c + Rzy * s, nzy = Rzy * c - Rzx * s;
+          Rxx = nxx; Rxy = nxy; Ryx = nyx; Ryy = nyy; Rzx = nzx; Rzy = nzy;
+        } else {  // about local y
+          ax[i] = Rxy; ay[i] = Ryy; az[i] = Rzy;
+          S nxx = Rxx * c - Rxz * s, nxz = Rxz * c + Rxx * s;
+          S nyx = Ryx * c - Ryz * s, nyz = Ryz * c + Ryx * s;
+          S nzx = Rzx * c - Rzz * s, nzz = Rzz * c + Rzx * s;
+          Rxx = nxx; Rxz = nxz; Ryx = nyx; Ryz = nyz; Rzx = nzx; Rzz = nzz;
+        }
+        px = px + d[i] * Rxz;
+        py = py + d[i] * Ryz;
+        pz = pz + d[i] * Rzz;
+      }
+      // tip velocity = sum_i (a_i x (p - o_i)) qd_i ; keep the Jacobian columns
+      S Jx[7], Jy[7], Jz[7];
+      S tvx = 0.0 * px, tvy = tvx, tvz = tvx;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        S dx = px - ox[i], dy = py - oy[i], dz = pz - oz[i];
+        Jx[i] = ay[i] * dz - az[i] * dy;
+        Jy[i] = az[i] * dx - ax[i] * dz;
+        Jz[i] = ax[i] * dy - ay[i] * dx;
+        tvx = tvx + Jx[i] * v[i];
+        tvy = tvy + Jy[i] * v[i];
+        tvz = tvz + Jz[i] * v[i];
+      }
+      // ---- ball state ----
+      const S* w = v + 7;   // ball angular velocity (world)
+      const S* bv = v + 10; // ball linear velocity
+      S bx_ = q[11], by_ = q[12], bz_ = q[13];
+      S fbx = 0.0 * px, fby = fbx, fbz = fbx - mb * g;  // force on ball
+      S tbx = 0.0 * px, tby = tbx, tbz = tbx;           // torque on ball (world)
+      S ftx = 0.0 * px, fty = ftx, ftz = ftx;           // force on tool tip
+      // tip sphere vs ball
+      {
+        S nx = bx_ - px, ny = by_ - py, nz = bz_ - pz;
+        S dist = sqrt_(nx * nx + ny * ny + nz * nz + 1e-12);
+        S depth = (rt + rb) - dist;
+        if (val(depth) > 0.0) {
+          nx = nx / dist; ny = ny / dist; nz = nz / dist;  // tip -> ball
+          const double Re = rt * rb / (rt + rb);
+          S Fn = sphere_plane_force(depth, Re, E);
+          // relative velocity of ball surface point w.r.t. tip at the contact
+          S cxr = -(rb)*nx, cyr = -(rb)*ny, czr = -(rb)*nz;  // contact point rel. ball centre
+          S rvx = bv[0] + (w[1] * czr - w[2] * cyr) - tvx;
+          S rvy = bv[1] + (w[2] * cxr - w[0] * czr) - tvy;
+          S rvz = bv[2] + (w[0] * cyr - w[1] * cxr) - tvz;
+          S vn = rvx * nx + rvy * ny + rvz * nz;
+          S tx = rvx - vn * nx, ty = rvy - vn * ny, tz = rvz - vn * nz;
+          S sl = sqrt_(tx * tx + ty * ty + tz * tz + vs * vs);
+          S cfx = Fn * nx - (mu * Fn) * tx / sl;
+          S cfy = Fn * ny - (mu * Fn) * ty / sl;
+          S cfz = Fn * nz - (mu * Fn) * tz / sl;
+          fbx = fbx + cfx; fby = fby + cfy; fbz = fbz + cfz;
+          tbx = tbx + (cyr * cfz - czr * cfy);
+          tby = tby + (czr * cfx - cxr * cfz);
+          tbz = tbz + (cxr * cfy - cyr * cfx);
+          ftx = ftx - cfx; fty = fty - cfy; ftz = ftz - cfz;
+        }
+      }
+      // ball vs table (z = 0)
+      {
+        S depth = rb - bz_;
+        if (val(depth) > 0.0) {
+          S Fn = sphere_plane_force(depth, rb, E);
+          // contact point velocity: v + w x (0,0,-rb)
+          S cvx = bv[0] - w[1] * rb;
+          S cvy = bv[1] + w[0] * rb;
+          S sl = sqrt_(cvx * cvx + cvy * cvy + vs * vs);
+          S fx_ = -(mu * Fn) * cvx / sl, fy_ = -(mu * Fn) * cvy / sl;
+          fbx = fbx + fx_; fby = fby + fy_; fbz = fbz + Fn;
+          // torque = (0,0,-rb) x (fx, fy, Fn)
+          tbx = tbx + rb * fy_;
+          tby = tby - rb * fx_;
+        }
+      }
+      // ---- accelerations, semi-implicit Euler ----
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        S tau = u[i] + Jx[i] * ftx + Jy[i] * fty + Jz[i] * ftz - bj * v[i];
+        v[i] = v[i] + (h / Ij) * tau;
+      }
+      v[7] = v[7] + (h / Ib) * tbx;
+      v[8] = v[8] + (h / Ib) * tby;
+      v[9] = v[9] + (h / Ib) * tbz;
+      v[10] = v[10] + (h / mb) * fbx;
+      v[11] = v[11] + (h / mb) * fby;
+      v[12] = v[12] + (h / mb) * fbz;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) q[i] = q[i] + h * v[i];
+      // quaternion rate for world-frame angular velocity: qdot = 0.5 * (0,w) (x) q
+      S qw = q[7], qx = q[8], qy = q[9], qz = q[10];
+      q[7] = qw + (0.5 * h) * (-(v[7] * qx) - v[8] * qy - v[9] * qz);
+      q[8] = qx + (0.5 * h) * (v[7] * qw + v[8] * qz - v[9] * qy);
+      q[9] = qy + (0.5 * h) * (v[8] * qw + v[9] * qx - v[7] * qz);
+      q[10] = qz + (0.5 * h) * (v[9] * qw + v[7] * qy - v[8] * qx);
+      q[11] = q[11] + h * v[10];
+      q[12] = q[12] + h * v[11];
+      q[13] = q[13] + h * v[12];
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) xn[i] = q[i];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) xn[14 + i] = v[i];
+  }
+};
+
+// ------------------------------------------------------------------------------
+// Test stub used by the survey probe: x+ = A x + B u + 0.01 sin(x), any (n, m).
+// p = [dt (unused), A row-major (n*n), B row-major (n*m)]
+template <int N_, int M_>
+struct AffineSin {
+  static constexpr int n = N_, m = M_, np = 1 + N_ * N_ + N_ * M_;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    const double* A = p + 1;
+    const double* B = p + 1 + N_ * N_;
+    for (int i = 0; i < N_; ++i) {
+      S s, c;
+      sincos_(x[i], &s, &c);
+      (void)c;
+      S acc = 0.01 * s;
+      for (int j = 0; j < N_; ++j) acc = acc + A[i * N_ + j] * x[j];
+      for (int j = 0; j < M_; ++j) acc = acc + B[i * M_ + j] * u[j];
+      xn[i] = acc;
+    }
+  }
+};
+
+// Dispatch a functor templated on the model type.
+#define DDP_MODEL_SWITCH(id, CALL)                                   \
+  switch (id) {                                                      \
+    case ::ddp::MODEL_PENDULUM: { typedef ::ddp::Pendulum Model; CALL; } break;           \
+    case ::ddp::MODEL_ACROBOT: { typedef ::ddp::Acrobot Model; CALL; } break;             \
+    case ::ddp::MODEL_CARTPOLE: { typedef ::ddp::CartPole Model; CALL; } break;           \
+    case ::ddp::MODEL_CARTPOLE_WALL: { typedef ::ddp::CartPoleWall Model; CALL; } break;  \
+    case ::ddp::MODEL_QUADRUPED: { typedef ::ddp::Quadruped Model; CALL; } break;         \
+    case ::ddp::MODEL_ARM_BALL: { typedef ::ddp::ArmBall Model; CALL; } break;            \
+    case ::ddp::MODEL_AFFINE_SIN_4_1: { typedef ::ddp::AffineSin<4, 1> Model; CALL; } break;     \
+    case ::ddp::MODEL_AFFINE_SIN_6_2: { typedef ::ddp::AffineSin<6, 2> Model; CALL; } break;     \
+    case ::ddp::MODEL_AFFINE_SIN_27_7: { typedef ::ddp::AffineSin<27, 7> Model; CALL; } break;   \
+    case ::ddp::MODEL_AFFINE_SIN_36_12: { typedef ::ddp::AffineSin<36, 12> Model; CALL; } break; \
+    case ::ddp::MODEL_AFFINE_SIN_37_12: { typedef ::ddp::AffineSin<37, 12> Model; CALL; } break; \
+    default: return -1;                                              \
+  }
+
+}  // namespace ddp

@@ -1,0 +1,351 @@
+"""Host side of the B200 iLQR: the reference's solver class surface over the CUDA C ABI.
+
+``IterativeLinearQuadraticRegulator`` keeps the constructor, setters, ``Solve()`` return
+tuple, ``SaveSolution`` and public attributes of /root/reference/ilqr.py:12-733 so the
+reference's example scripts can switch to it; ``BatchedILQR`` is the same solver for B
+independent trajectories (MPC resolves, initial-condition seeds), which is what the GPU is
+for.  All arithmetic happens in ``libddp_b200.so`` (hand-written sm_100a kernels); torch
+only provides device memory and the stream.  There is no CPU path: constructing a solver
+without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+
+import numpy as np
+
+from . import _lib
+from .utils_derivs_interpolation import derivs_interpolation
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _as_system(system):
+    """Accept a native AnalyticSystem (has model_id/params).  A Drake System cannot be
+    evaluated in-kernel; point the user at drake_ddp_b200.systems."""
+    if hasattr(system, "model_id") and hasattr(system, "params"):
+        return system
+    raise TypeError(
+        "system must be a drake_ddp_b200.systems.AnalyticSystem (fixed analytic model evaluated "
+        "in-kernel); Drake Systems are not evaluated on the GPU path -- build the matching model "
+        "with drake_ddp_b200.systems.<model>()")
+
+
+class BatchedILQR:
+    """B independent iLQR problems sharing one model, horizon and cost."""
+
+    def __init__(self, system, num_timesteps, batch=1, delta=1e-2, beta=0.95, gamma=0.0,
+                 derivs_keypoint_method=None, ls_parallel=None, device=None):
+        import torch
+
+        L = _lib.lib()  # raises if the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("drake_ddp_b200 needs a CUDA device (no CPU fallback)")
+        self._torch = torch
+        self._L = L
+        self.system = _as_system(system)
+        self.N, self.B = int(num_timesteps), int(batch)
+        self.n, self.m = self.system.n, self.system.m
+        self.T = self.N - 1
+        self.delta, self.beta, self.gamma = float(delta), float(beta), float(gamma)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        n, m, npar = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(L.ddp_model_dims(self.system.model_id, ctypes.byref(n), ctypes.byref(m),
+                                    ctypes.byref(npar)), "ddp_model_dims")
+        assert (n.value, m.value) == (self.n, self.m), "system dims do not match the compiled model"
+        params = np.ascontiguousarray(self.system.params, dtype=np.float64)
+        assert params.size == npar.value, f"model expects {npar.value} parameters, got {params.size}"
+        n_eps = 0
+        eps = 1.0
+        while eps >= 1e-8:
+            n_eps += 1
+            eps *= self.beta
+        if ls_parallel is None:
+            ls_parallel = 8 if self.B <= 64 else (2 if self.B <= 512 else 1)
+        self.A = max(1, min(int(ls_parallel), n_eps))
+        nbytes = L.ddp_workspace_bytes(self.system.model_id, self.N, self.B, self.A)
+        assert nbytes > 0, "bad (model, N, B, A)"
+        with torch.cuda.device(self.device):
+            self._arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._stream = torch.cuda.current_stream(self.device)
+            h = ctypes.c_void_p()
+            _lib.check(L.ddp_create(ctypes.byref(h), self.system.model_id, _ptr(params), params.size,
+                                    self.N, self.B, self.A, ctypes.c_void_p(self._arena.data_ptr()),
+                                    nbytes, ctypes.c_void_p(self._stream.cuda_stream)), "ddp_create")
+        self._h = h
+        _lib.check(L.ddp_set_options(h, self.delta, self.beta, self.gamma), "ddp_set_options")
+        self.set_keypoint_method(derivs_keypoint_method)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and self._L is not None:
+            try:
+                self._L.ddp_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- configuration ------------------------------------------------------------------
+    def set_keypoint_method(self, cfg):
+        """derivs_keypoint_method of the reference ctor (ilqr.py:97-100)."""
+        if cfg is None:
+            cfg = derivs_interpolation("setInterval", 1, 0, 0, 0)
+        if cfg.keypoint_method not in _lib.KP_METHODS:
+            raise Exception("unknown interpolation method")  # ilqr.py:404
+        self.derivs_interpolation = cfg
+        _lib.check(self._L.ddp_set_keypoints(self._h, _lib.KP_METHODS[cfg.keypoint_method], int(cfg.minN),
+                                             int(cfg.maxN), float(cfg.jerk_threshold),
+                                             float(cfg.iterative_error_threshold)), "ddp_set_keypoints")
+
+    def set_cost(self, Q, R, Qf):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        R = np.ascontiguousarray(R, dtype=np.float64)
+        Qf = np.ascontiguousarray(Qf, dtype=np.float64)
+        assert Q.shape == (self.n, self.n) and R.shape == (self.m, self.m) and Qf.shape == (self.n, self.n)
+        _lib.check(self._L.ddp_set_cost(self._h, _ptr(Q), _ptr(R), _ptr(Qf)), "ddp_set_cost")
+
+    def set_target(self, x_nom):
+        x_nom = np.ascontiguousarray(x_nom, dtype=np.float64)
+        per = 1 if x_nom.ndim == 2 else 0
+        assert x_nom.shape[-1] == self.n and (not per or x_nom.shape[0] == self.B)
+        _lib.check(self._L.ddp_set_target(self._h, _ptr(x_nom), per), "ddp_set_target")
+
+    def set_initial_state(self, x0):
+        """x0: (B, n) or (n,) broadcast."""
+        x0 = np.asarray(x0, dtype=np.float64)
+        if x0.ndim == 1:
+            x0 = np.broadcast_to(x0, (self.B, self.n))
+        x0 = np.ascontiguousarray(x0)
+        assert x0.shape == (self.B, self.n)
+        _lib.check(self._L.ddp_set_initial_state(self._h, _ptr(x0)), "ddp_set_initial_state")
+
+    def set_initial_guess(self, u_guess):
+        """u_guess: (B, T, m) device layout, or the reference's (m, T) broadcast over the batch."""
+        u = np.asarray(u_guess, dtype=np.float64)
+        if u.ndim == 2:
+            assert u.shape == (self.m, self.T)
+            u = np.broadcast_to(u.T, (self.B, self.T, self.m))
+        u = np.ascontiguousarray(u)
+        assert u.shape == (self.B, self.T, self.m)
+        _lib.check(self._L.ddp_set_initial_guess(self._h, _ptr(u)), "ddp_set_initial_guess")
+
+    def set_initial_pinned(self, x0_pinned, u_pinned):
+        """Same as the two setters above but from caller-owned (pinned) buffers, no reshaping."""
+        _lib.check(self._L.ddp_set_initial_state(self._h, ctypes.c_void_p(x0_pinned.data_ptr())), "x0")
+        _lib.check(self._L.ddp_set_initial_guess(self._h, ctypes.c_void_p(u_pinned.data_ptr())), "u")
+
+    def reset(self):
+        _lib.check(self._L.ddp_reset(self._h), "ddp_reset")
+
+    # ---- solve ----------------------------------------------------------------------------
+    def begin_solve(self):
+        _lib.check(self._L.ddp_begin_solve(self._h), "ddp_begin_solve")
+
+    def iterate(self) -> int:
+        """One forward + backward pass for every unconverged trajectory; returns #still active."""
+        n_active = ctypes.c_int()
+        _lib.check(self._L.ddp_iterate(self._h, ctypes.byref(n_active)), "ddp_iterate")
+        return n_active.value
+
+    def iterate_async(self):
+        _lib.check(self._L.ddp_iterate_async(self._h), "ddp_iterate_async")
+
+    def sync(self):
+        _lib.check(self._L.ddp_sync(self._h), "ddp_sync")
+
+    def solve(self, max_iters=0) -> int:
+        it = ctypes.c_int()
+        _lib.check(self._L.ddp_solve(self._h, int(max_iters), ctypes.byref(it)), "ddp_solve")
+        return it.value
+
+    def run_phase(self, phase: int):
+        _lib.check(self._L.ddp_run_phase(self._h, phase), "ddp_run_phase")
+
+    # ---- array access -------------------------------------------------------------------
+    _SHAPES = {
+        _lib.X_BAR: lambda s: (s.B, s.N, s.n), _lib.U_BAR: lambda s: (s.B, s.T, s.m),
+        _lib.K: lambda s: (s.B, s.T, s.m, s.n), _lib.KAPPA: lambda s: (s.B, s.T, s.m),
+        _lib.DV: lambda s: (s.B, s.T), _lib.FX: lambda s: (s.B, s.T, s.n, s.n),
+        _lib.FU: lambda s: (s.B, s.T, s.n, s.m), _lib.COST: lambda s: (s.B,),
+        _lib.EPS: lambda s: (s.B,), _lib.IMPROVEMENT: lambda s: (s.B,),
+        _lib.X0: lambda s: (s.B, s.n), _lib.X_NOM: lambda s: (s.B, s.n),
+        _lib.CAND_COST: lambda s: (s.B, s.A), _lib.CAND_EXPECTED: lambda s: (s.B, s.A),
+        _lib.CAND_X: lambda s: (s.B, s.A, s.N, s.n), _lib.CAND_U: lambda s: (s.B, s.A, s.T, s.m),
+    }
+
+    def get(self, which: int) -> np.ndarray:
+        out = np.empty(self._SHAPES[which](self), dtype=np.float64)
+        _lib.check(self._L.ddp_get(self._h, which, _ptr(out)), "ddp_get")
+        return out
+
+    def get_into(self, which: int, dst_pinned):
+        _lib.check(self._L.ddp_get(self._h, which, ctypes.c_void_p(dst_pinned.data_ptr())), "ddp_get")
+
+    def put(self, which: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.shape == self._SHAPES[which](self), (arr.shape, self._SHAPES[which](self))
+        _lib.check(self._L.ddp_put(self._h, which, _ptr(arr)), "ddp_put")
+
+    def get_int(self, which: int) -> np.ndarray:
+        shape = (self.B, self.T) if which == _lib.I_KEYPOINTS else (self.B,)
+        out = np.empty(shape, dtype=np.int32)
+        _lib.check(self._L.ddp_get_int(self._h, which, _ptr(out)), "ddp_get_int")
+        return out
+
+    def device_tensor(self, which: int):
+        """Zero-copy torch view of an arena array (e.g. COST for an NCCL all-gather)."""
+        torch = self._torch
+        ptr = self._L.ddp_device_ptr(self._h, which)
+        off = ptr - self._arena.data_ptr()
+        nelem = self._L.ddp_array_elems(self._h, which)
+        return self._arena[off: off + 8 * nelem].view(torch.float64).view(self._SHAPES[which](self))
+
+    def keypoints(self):
+        cnt = self.get_int(_lib.I_NUM_KEYPOINTS)
+        kp = self.get_int(_lib.I_KEYPOINTS)
+        return [list(map(int, kp[b, :cnt[b]])) for b in range(self.B)]
+
+    def timings_ms(self):
+        ms = (ctypes.c_float * 4)()
+        _lib.check(self._L.ddp_last_timings(self._h, ms), "ddp_last_timings")
+        return {"linesearch": ms[0], "derivs": ms[1], "backward": ms[2], "iteration": ms[3]}
+
+    def launch_count(self) -> int:
+        return int(self._L.ddp_launch_count(self._h))
+
+    # convenience getters in device layout
+    @property
+    def cost(self):
+        return self.get(_lib.COST)
+
+    @property
+    def status(self):
+        return self.get_int(_lib.I_STATUS)
+
+
+class IterativeLinearQuadraticRegulator:
+    """Drop-in for the reference class (/root/reference/ilqr.py:12): same constructor
+    signature, setters, ``Solve()`` and result attributes; one trajectory (B=1)."""
+
+    def __init__(self, system, num_timesteps, input_port_index=0, delta=1e-2, beta=0.95, gamma=0.0,
+                 derivs_keypoint_method=None, ls_parallel=None):
+        self.system = _as_system(system)
+        self.N = num_timesteps
+        self.delta, self.beta, self.gamma = delta, beta, gamma
+        self.n, self.m = self.system.n, self.system.m
+        self._core = BatchedILQR(self.system, num_timesteps, batch=1, delta=delta, beta=beta,
+                                 gamma=gamma, derivs_keypoint_method=derivs_keypoint_method,
+                                 ls_parallel=ls_parallel)
+        self.derivs_interpolation = self._core.derivs_interpolation
+        # ilqr.py:61-67
+        self.x0 = np.zeros(self.n)
+        self.Q, self.R, self.Qf = np.eye(self.n), np.eye(self.m), np.eye(self.n)
+        self._u_guess = None
+        self.time_getDerivs = 0
+        self.percentage_derivs = 0
+        self.time_backwardsPass = 0
+        self.time_fp = 0
+
+    # ---- setters: keep references, upload at Solve() like the reference reads them then ----
+    def SetInitialState(self, x0):
+        self.x0 = x0
+
+    def SetTargetState(self, x_nom):
+        self.x_nom = np.asarray(x_nom).reshape((self.n,))
+
+    def SetRunningCost(self, Q, R):
+        assert Q.shape == (self.n, self.n)
+        assert R.shape == (self.m, self.m)
+        self.Q = Q
+        self.R = R
+
+    def SetTerminalCost(self, Qf):
+        assert Qf.shape == (self.n, self.n)
+        self.Qf = Qf
+
+    def SetInitialGuess(self, u_guess):
+        assert u_guess.shape == (self.m, self.N - 1)
+        self._u_guess = u_guess
+
+    def SetControlLimits(self, u_min, u_max):
+        pass  # no-op in the reference too (ilqr.py:158-159)
+
+    # ---- results in the reference's layouts (time last, ilqr.py:70-83) ---------------------
+    @property
+    def x_bar(self):
+        return np.ascontiguousarray(self._core.get(_lib.X_BAR)[0].T)
+
+    @property
+    def u_bar(self):
+        return np.ascontiguousarray(self._core.get(_lib.U_BAR)[0].T)
+
+    @property
+    def kappa(self):
+        return np.ascontiguousarray(self._core.get(_lib.KAPPA)[0].T)
+
+    @property
+    def K(self):
+        return np.ascontiguousarray(self._core.get(_lib.K)[0].transpose(1, 2, 0))
+
+    @property
+    def fx(self):
+        return np.ascontiguousarray(self._core.get(_lib.FX)[0].transpose(1, 2, 0))
+
+    @property
+    def fu(self):
+        return np.ascontiguousarray(self._core.get(_lib.FU)[0].transpose(1, 2, 0))
+
+    @property
+    def dV_coeff(self):
+        return self._core.get(_lib.DV)[0].copy()
+
+    def _upload(self):
+        c = self._core
+        c.set_cost(self.Q, self.R, self.Qf)
+        c.set_target(self.x_nom)
+        c.set_initial_state(np.asarray(self.x0, dtype=np.float64).reshape(self.n))
+        if self._u_guess is not None:
+            c.set_initial_guess(self._u_guess)
+            self._u_guess = None  # afterwards u_bar lives on the device (ilqr.py:375)
+
+    def Solve(self):
+        """ilqr.py:669-710: returns (x (n,N), u (m,N-1), solve_time, optimal_cost)."""
+        c = self._core
+        self._upload()
+        print("----------------------------------------------------------------------------------------------------------------------------------")
+        print("|    iter    |    cost    |    eps    |    ls    | derivs time | derivs '%'  | bp time  | fp time  |   iter time    |    time    |")
+        print("----------------------------------------------------------------------------------------------------------------------------------")
+        c.begin_solve()
+        i = 1
+        st = time.time()
+        n_active = 1
+        total_time = 0.0
+        while n_active > 0:
+            st_iter = time.time()
+            n_active = c.iterate()
+            status = int(c.get_int(_lib.I_STATUS)[0])
+            ls_iters = int(c.get_int(_lib.I_LS_ITERS)[0])
+            if status == _lib.TRAJ_LINESEARCH_FAILED:
+                raise RuntimeError("linesearch failed after %s iterations" % ls_iters)  # ilqr.py:337
+            L_new = float(c.get(_lib.COST)[0])
+            eps = float(c.get(_lib.EPS)[0])
+            ms = c.timings_ms()
+            self.time_fp = ms["linesearch"] * 1e-3
+            self.time_getDerivs = ms["derivs"] * 1e-3
+            self.time_backwardsPass = ms["backward"] * 1e-3
+            self.percentage_derivs = (int(c.get_int(_lib.I_NUM_KEYPOINTS)[0]) / (self.N - 1)) * 100
+            iter_time = time.time() - st_iter
+            total_time = time.time() - st
+            print(f"{i:^14}{L_new:11.4f}  {eps:^12.4f}{ls_iters:^11}   {self.time_getDerivs:1.5f}         {self.percentage_derivs:.1f}       {self.time_backwardsPass:1.5f}    {self.time_fp:1.5f}      {iter_time:1.5f}          {total_time:4.2f}")
+            i += 1
+        return self.x_bar, self.u_bar, total_time, L_new
+
+    def SaveSolution(self, fname):
+        """ilqr.py:712-733: npz with t, x_bar[:, :-1], u_bar, K."""
+        dt = self.system.GetSubsystemByName("plant").time_step()
+        T = (self.N - 1) * dt
+        t = np.arange(0, T, dt)
+        np.savez(fname, t=t, x_bar=self.x_bar[:, :-1], u_bar=self.u_bar, K=self.K)
