@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the UNMODIFIED reference
+solver (/root/reference/ilqr.py, imported through oracle/pydrake_shim.py) on this repo's
+analytic models.  Only runs where /root/reference exists; the fixtures are committed so the
+GPU box (which has no reference tree) can check both the oracle port and the CUDA path
+against the reference's own outputs.
+
+    python -m oracle.make_golden
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from drake_ddp_b200 import problems  # noqa: E402
+from drake_ddp_b200.utils_derivs_interpolation import derivs_interpolation  # noqa: E402
+from oracle.pydrake_shim import ShimSystem, load_reference_ilqr  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# name -> (problem factory, keypoint cfg or None, iterations)
+CASES = {
+    "pendulum_N100": (lambda: problems.pendulum(100), None, 5),
+    "acrobot_N40": (lambda: problems.acrobot(40), None, 6),
+    "cart_pole_N60": (lambda: problems.cart_pole(60), None, 6),
+    "wall_N60": (lambda: problems.cart_pole_with_wall(60), None, 5),
+    "affine_4_1_setInterval5": (lambda: problems.affine_sin(4, 1, 40),
+                                derivs_interpolation("setInterval", 5, 0, 0, 0), 3),
+    "affine_4_1_adaptiveJerk": (lambda: problems.affine_sin(4, 1, 40),
+                                derivs_interpolation("adaptiveJerk", 2, 10, 1e-4, 0), 3),
+    "affine_4_1_iterativeError": (lambda: problems.affine_sin(4, 1, 40),
+                                  derivs_interpolation("iterativeError", 2, 0, 0, 1e-9), 3),
+    "affine_27_7_N30": (lambda: problems.affine_sin(27, 7, 30), None, 3),
+    "quadruped_N30": (lambda: problems.quadruped(30), None, 3),
+    "quadruped_N30_adaptiveJerk": (lambda: problems.quadruped(30),
+                                   derivs_interpolation("adaptiveJerk", 2, 20, 0.3, 10), 3),
+}
+
+
+def run_reference(prob, kp, iters):
+    ref, ref_utils = load_reference_ilqr()
+    method = None if kp is None else ref_utils.derivs_interpolation(
+        kp.keypoint_method, kp.minN, kp.maxN, kp.jerk_threshold, kp.iterative_error_threshold)
+    r = ref.IterativeLinearQuadraticRegulator(ShimSystem(prob.system), prob.N, delta=prob.delta,
+                                              beta=prob.beta, gamma=prob.gamma,
+                                              derivs_keypoint_method=method)
+    r.SetInitialState(prob.x0.copy())
+    r.SetTargetState(prob.x_nom)
+    r.SetRunningCost(prob.Q, prob.R)
+    r.SetTerminalCost(prob.Qf)
+    r.SetInitialGuess(prob.u_guess.copy())
+    L, costs, epss, lss, pct = np.inf, [], [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(iters):     # the body of Solve()'s loop, ilqr.py:695-697
+            L, eps, ls = r._forward_pass(L)
+            r._backward_pass()
+            costs.append(L), epss.append(eps), lss.append(ls), pct.append(r.percentage_derivs)
+    return dict(costs=np.array(costs), eps=np.array(epss), ls_iters=np.array(lss),
+                percentage_derivs=np.array(pct), x_bar=r.x_bar, u_bar=r.u_bar, K=r.K,
+                kappa=r.kappa, dV_coeff=r.dV_coeff, fx=r.fx, fu=r.fu)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, (factory, kp, iters) in CASES.items():
+        prob = factory()
+        out = run_reference(prob, kp, iters)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), iters=iters, **out)
+        print(name, "costs", out["costs"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (called through the C ABI) against the CPU oracle and against the
+reference-generated fixtures in tests/golden/.  Tolerances: the north star asks for 1e-5
+relative on cost and 1e-4 on K, kappa; fp64 end to end gives far better, so the per-iteration
+checks below use 1e-9 on cost and 1e-6 on gains, and discrete decisions (accepted eps,
+ls_iters, keypoints) must be identical."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from drake_ddp_b200 import _lib, problems
+from drake_ddp_b200.utils_derivs_interpolation import derivs_interpolation
+from oracle import ilqr_port
+from oracle.make_golden import CASES
+from tests.helpers import gpu_state, make_gpu, make_oracle, relerr
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+COST_RTOL, GAIN_RTOL = 1e-9, 1e-6
+
+
+def check_state(s, o, b=0, tol=GAIN_RTOL):
+    x, u, K, kappa, dV, fx, fu = gpu_state(s, b)
+    uscale = max(1.0, np.abs(o.u_bar).max())
+    assert relerr(x, o.x_bar) < tol
+    assert np.abs(u - o.u_bar).max() < tol * uscale
+    assert relerr(K, o.K) < tol
+    assert np.abs(kappa - o.kappa).max() < tol * max(uscale, np.abs(o.kappa).max())
+    assert np.abs(dV - o.dV).max() < tol * max(1.0, np.abs(o.dV).max())
+    assert relerr(fx, o.fx) < tol and relerr(fu, o.fu) < tol
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_matches_reference_golden(name):
+    factory, kp, iters = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s = make_gpu(factory(), kp=kp)
+    s.begin_solve()
+    for i in range(iters):
+        s.iterate()
+        assert abs(s.cost[0] - g["costs"][i]) <= 1e-8 * abs(g["costs"][i])
+        assert s.get(_lib.EPS)[0] == g["eps"][i]
+        assert s.get_int(_lib.I_LS_ITERS)[0] == g["ls_iters"][i]
+    x, u, K, kappa, dV, fx, fu = gpu_state(s)
+    assert relerr(x.T, g["x_bar"]) < 1e-7
+    assert relerr(K.transpose(1, 2, 0), g["K"]) < 1e-6         # north star: 1e-4
+    assert np.abs(kappa.T - g["kappa"]).max() < 1e-6 * max(1.0, np.abs(g["u_bar"]).max())
+    assert relerr(fx.transpose(1, 2, 0), g["fx"]) < 1e-7
+    assert abs(100.0 * s.get_int(_lib.I_NUM_KEYPOINTS)[0] / (s.N - 1) - g["percentage_derivs"][-1]) < 1e-9
+
+
+PER_ITER = [
+    ("pendulum", lambda: problems.pendulum(100), None, 5),
+    ("acrobot", lambda: problems.acrobot(40), None, 5),
+    ("cart_pole", lambda: problems.cart_pole(100), None, 4),
+    ("wall", lambda: problems.cart_pole_with_wall(100), None, 3),
+    ("affine_6_2", lambda: problems.affine_sin(6, 2, 30), None, 3),
+    ("affine_37_12", lambda: problems.affine_sin(37, 12, 30), None, 3),
+    ("affine_36_12_jerk", lambda: problems.affine_sin(36, 12, 40), derivs_interpolation("adaptiveJerk", 2, 10, 1e-4, 0), 3),
+    ("affine_27_7_ie", lambda: problems.affine_sin(27, 7, 40), derivs_interpolation("iterativeError", 2, 0, 0, 1e-9), 3),
+    ("quadruped", lambda: problems.quadruped(50), None, 4),
+    ("quadruped_interval", lambda: problems.quadruped(50), derivs_interpolation("setInterval", 4, 0, 0, 0), 3),
+    ("quadruped_ie", lambda: problems.quadruped(40), derivs_interpolation("iterativeError", 2, 0, 0, 1e-7), 3),
+]
+
+
+@pytest.mark.parametrize("name,factory,kp,iters", PER_ITER, ids=[p[0] for p in PER_ITER])
+def test_gpu_matches_oracle_per_iteration(name, factory, kp, iters):
+    prob = factory()
+    s, o = make_gpu(prob, kp=kp), make_oracle(prob, kp=kp)
+    s.begin_solve()
+    L = np.inf
+    for i in range(iters):
+        s.iterate()
+        rec = o.iterate(L)
+        L = rec.L
+        assert abs(s.cost[0] - rec.L) <= COST_RTOL * abs(rec.L), (i, s.cost[0], rec.L)
+        assert s.get(_lib.EPS)[0] == rec.eps
+        assert s.get_int(_lib.I_LS_ITERS)[0] == rec.ls_iters
+        assert s.keypoints()[0] == rec.keypoints
+        check_state(s, o)
+
+
+@pytest.mark.parametrize("n,m,N", [(4, 1, 20), (6, 2, 25), (27, 7, 12), (36, 12, 10), (37, 12, 10)])
+def test_backward_pass_teacher_forced(n, m, N):
+    """Feed identical fx, fu, x_bar, u_bar and a DENSE (non-diagonal) cost to ilqr._backward_pass's
+    restatement and to the kernel; compare K, kappa, dV."""
+    rng = np.random.default_rng(n * 100 + m)
+    prob = problems.affine_sin(n, m, N)
+    T = N - 1
+
+    def spd(k, scale):
+        A = rng.standard_normal((k, k))
+        return scale * (A @ A.T / k + np.eye(k))
+
+    prob.Q, prob.R, prob.Qf = spd(n, 0.1), spd(m, 0.05), spd(n, 2.0)
+    B = 3
+    s = make_gpu(prob, B=B)
+    fx = np.eye(n)[None, None] + 0.1 * rng.standard_normal((B, T, n, n))
+    fu = 0.3 * rng.standard_normal((B, T, n, m))
+    xb, ub = rng.standard_normal((B, N, n)), rng.standard_normal((B, T, m))
+    for which, arr in ((_lib.FX, fx), (_lib.FU, fu), (_lib.X_BAR, xb), (_lib.U_BAR, ub)):
+        s.put(which, arr)
+    s.run_phase(_lib.PHASE_BACKWARD)
+    for b in range(B):
+        o = make_oracle(prob)
+        o.fx, o.fu, o.x_bar, o.u_bar = fx[b].copy(), fu[b].copy(), xb[b].copy(), ub[b].copy()
+        o.backward_pass()
+        assert relerr(s.get(_lib.K)[b], o.K) < 1e-9
+        assert relerr(s.get(_lib.KAPPA)[b], o.kappa) < 1e-9
+        assert relerr(s.get(_lib.DV)[b], o.dV) < 1e-9
+
+
+@pytest.mark.parametrize("name,A", [("pendulum", 8), ("quadruped", 4), ("affine", 27)])
+def test_linesearch_teacher_forced(name, A):
+    """Identical x_bar, u_bar, K, kappa, dV, L_last on both sides: candidate costs, expected
+    improvements, the first-satisfying pick and the committed trajectory must agree."""
+    rng = np.random.default_rng(7)
+    prob = {"pendulum": lambda: problems.pendulum(40), "quadruped": lambda: problems.quadruped(30),
+            "affine": lambda: problems.affine_sin(6, 2, 30)}[name]()
+    n, m, N, T = prob.system.n, prob.system.m, prob.N, prob.N - 1
+    o = make_oracle(prob)
+    r0 = o.iterate(np.inf)                      # a sensible x_bar/u_bar/K/kappa/dV to start from
+    o.kappa = o.kappa * 6.0                     # overshoot so eps=1 is rejected sometimes
+    s = make_gpu(prob, A=A)
+    for which, arr in ((_lib.X_BAR, o.x_bar), (_lib.U_BAR, o.u_bar), (_lib.K, o.K), (_lib.KAPPA, o.kappa),
+                       (_lib.DV, o.dV)):
+        s.put(which, arr[None])
+    s.put(_lib.COST, np.array([r0.L]))
+    s.run_phase(_lib.PHASE_LINESEARCH)
+    eps_o, x_o, u_o, L_o, ls_o = o.linesearch(r0.L)
+    assert s.get(_lib.EPS)[0] == eps_o and s.get_int(_lib.I_LS_ITERS)[0] == ls_o
+    assert relerr(s.get(_lib.X_BAR)[0], x_o) < 1e-10 and relerr(s.get(_lib.U_BAR)[0], u_o) < 1e-10
+    # every candidate of the last round against the oracle's rollout at the same eps
+    table = ilqr_port.eps_table(prob.beta)
+    base = ((ls_o - 1) // s.A) * s.A
+    Lc, Ec = s.get(_lib.CAND_COST)[0], s.get(_lib.CAND_EXPECTED)[0]
+    for ai in range(min(s.A, len(table) - base)):
+        _, _, L_ref, E_ref = o.rollout(table[base + ai])
+        assert abs(Lc[ai] - L_ref) <= 1e-10 * abs(L_ref)
+        assert abs(Ec[ai] - E_ref) <= 1e-10 * max(1e-300, abs(E_ref))
+
+
+@pytest.mark.parametrize("kp", [derivs_interpolation("setInterval", 1, 0, 0, 0),
+                                derivs_interpolation("setInterval", 7, 0, 0, 0),
+                                derivs_interpolation("adaptiveJerk", 3, 9, 2e-3, 0),
+                                derivs_interpolation("iterativeError", 3, 0, 0, 1e-6)],
+                         ids=["every", "interval7", "jerk", "iterError"])
+def test_derivatives_teacher_forced(kp):
+    """_get_derivatives on a given (x, u): keypoints, exact Jacobians at keypoints, lerp between."""
+    rng = np.random.default_rng(11)
+    prob = problems.cart_pole_with_wall(60)
+    N, T = prob.N, prob.N - 1
+    x = prob.x0[None] + np.cumsum(0.05 * rng.standard_normal((N, 4)), axis=0)
+    u = 5.0 * rng.standard_normal((T, 1))
+    s, o = make_gpu(prob, kp=kp), make_oracle(prob, kp=kp)
+    s.put(_lib.X_BAR, x[None]); s.put(_lib.U_BAR, u[None])
+    s.run_phase(_lib.PHASE_DERIVATIVES)
+    kps = o.get_derivatives(x, u)
+    assert s.keypoints()[0] == kps
+    assert relerr(s.get(_lib.FX)[0], o.fx) < 1e-10 and relerr(s.get(_lib.FU)[0], o.fu) < 1e-10
+
+
+def test_batch_equals_independent_solves():
+    """Trajectories are independent: a batch of 6 seeds equals 6 single solves bit for bit, for
+    any number of line-search candidates evaluated per round."""
+    prob = problems.acrobot(40)
+    x0 = prob.batch_x0(6, seed=0)
+    big = make_gpu(prob, B=6, A=2, x0=x0)
+    big.solve(max_iters=6)
+    for b in range(6):
+        one = make_gpu(prob, B=1, A=5, x0=x0[b])
+        one.solve(max_iters=6)
+        assert one.cost[0] == big.cost[b]
+        np.testing.assert_array_equal(one.get(_lib.K)[0], big.get(_lib.K)[b])
+        assert one.get_int(_lib.I_ITERS)[0] == big.get_int(_lib.I_ITERS)[b]
+        o = make_oracle(prob, x0=x0[b])
+        o.solve(max_iters=6)
+        assert abs(o.trace[-1].L - big.cost[b]) <= 1e-8 * abs(big.cost[b])
+        assert len(o.trace) == big.get_int(_lib.I_ITERS)[b]
+
+
+def test_dropin_class_solve_and_save(tmp_path):
+    """The reference call sequence of pendulum.py:85-100 on the drop-in class."""
+    from ilqr import IterativeLinearQuadraticRegulator
+    prob = problems.pendulum(100)
+    ilqr = IterativeLinearQuadraticRegulator(prob.system, prob.N)
+    ilqr.SetInitialState(prob.x0)
+    ilqr.SetTargetState(prob.x_nom)
+    ilqr.SetRunningCost(prob.Q, prob.R)
+    ilqr.SetTerminalCost(prob.Qf)
+    ilqr.SetInitialGuess(prob.u_guess)
+    with contextlib.redirect_stdout(io.StringIO()) as f:
+        states, inputs, solve_time, optimal_cost = ilqr.Solve()
+    o = make_oracle(prob)
+    xo, uo, Lo = o.solve()
+    assert states.shape == (2, 100) and inputs.shape == (1, 99)
+    assert len(f.getvalue().strip().split("\n")) - 3 == len(o.trace)        # same iteration count
+    assert abs(optimal_cost - Lo) <= 1e-5 * abs(Lo)                          # north-star tolerance
+    assert relerr(states, xo.T) < 1e-7
+    assert relerr(ilqr.K, o.K.transpose(1, 2, 0)) < 1e-4 and ilqr.K.shape == (1, 2, 99)
+    assert ilqr.fx.shape == (2, 2, 99) and ilqr.fu.shape == (2, 1, 99) and ilqr.kappa.shape == (1, 99)
+    fname = str(tmp_path / "sol.npz")
+    ilqr.SaveSolution(fname)                                                 # ilqr.py:712-733
+    d = np.load(fname)
+    assert set(d.files) == {"t", "x_bar", "u_bar", "K"}
+    assert d["x_bar"].shape == (2, 99) and d["t"].shape == (99,) and d["K"].shape == (1, 2, 99)
+
+
+def test_mpc_resolve_keeps_stale_state():
+    """Receding-horizon resolves on the SAME object (acrobot.py:142-155): K, kappa, x_bar of the
+    previous solve feed the first rollout of the next one."""
+    from ilqr import IterativeLinearQuadraticRegulator
+    prob = problems.acrobot(40)
+    ilqr = IterativeLinearQuadraticRegulator(prob.system, prob.N, beta=prob.beta)
+    o = make_oracle(prob)
+    ilqr.SetTargetState(prob.x_nom); ilqr.SetRunningCost(prob.Q, prob.R); ilqr.SetTerminalCost(prob.Qf)
+    x0, u_guess, replan = prob.x0, prob.u_guess, 2
+    for resolve in range(3):
+        ilqr.SetInitialState(x0); ilqr.SetInitialGuess(u_guess)
+        with contextlib.redirect_stdout(io.StringIO()):
+            x, u, _, L = ilqr.Solve()
+        o.set_initial_state(x0); o.set_initial_guess(u_guess)
+        xo, uo, Lo = o.solve()
+        assert abs(L - Lo) <= 1e-7 * abs(Lo), resolve
+        assert relerr(x, xo.T) < 1e-6
+        u_guess = np.block([u[:, replan:], np.repeat(u[:, -1][np.newaxis].T, replan, axis=1)])
+        x0 = x[:, replan]
+
+
+def test_linesearch_failure_raises_like_reference():
+    """At an optimum no eps improves the cost: RuntimeError('linesearch failed after 27 iterations')."""
+    from ilqr import IterativeLinearQuadraticRegulator
+    prob = problems.affine_sin(4, 1, 40)
+    prob.delta = -1.0          # never stop on improvement -> must end in the line-search failure
+    ilqr = IterativeLinearQuadraticRegulator(prob.system, prob.N, beta=0.5, delta=prob.delta)
+    ilqr.SetInitialState(prob.x0); ilqr.SetTargetState(prob.x_nom)
+    ilqr.SetRunningCost(prob.Q, prob.R); ilqr.SetTerminalCost(prob.Qf); ilqr.SetInitialGuess(prob.u_guess)
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(RuntimeError, match="linesearch failed after 27 iterations"):
+            ilqr.Solve()
+    o = make_oracle(prob)
+    with pytest.raises(RuntimeError, match="linesearch failed after 27 iterations"):
+        o.solve()
+
+
+def test_infeasible_rollout_is_infinite_cost():
+    """Non-finite dynamics => L = inf for that candidate (ilqr.py:317-323); on the first iteration
+    inf - inf = nan is rejected for every eps, so the solve fails exactly like the reference."""
+    prob = problems.pendulum(20)
+    prob.u_guess = np.full((1, 19), 1e308)
+    s = make_gpu(prob, A=8)
+    s.begin_solve()
+    s.iterate()
+    assert s.status[0] == _lib.TRAJ_LINESEARCH_FAILED
+    assert np.all(np.isinf(s.get(_lib.CAND_COST)[0][:1]))
+    o = make_oracle(prob)
+    with pytest.raises(RuntimeError, match="linesearch failed after 360 iterations"):
+        o.solve()
+
+
+def test_full_size_c4_properties():
+    """BASELINE config C4 at full size (n=36, m=12, N=200, B=1024): size-independent properties
+    + spot checks against the oracle.  Duplicate seeds must give bit-identical results, accepted
+    steps must satisfy the acceptance test, costs must not increase."""
+    prob = problems.quadruped(200)
+    B = 1024
+    x0 = prob.batch_x0(B, seed=0)
+    x0[-4:] = x0[:4]
+    s = make_gpu(prob, B=B, A=2, x0=x0)
+    s.begin_solve()
+    prev = np.full(B, np.inf)
+    spot = [0, 1, 517]
+    oracles = [make_oracle(prob, x0=x0[b]) for b in spot]
+    Ls = [np.inf] * len(spot)
+    for it in range(2):
+        s.iterate()
+        cost, status = s.cost, s.status
+        ok = status != _lib.TRAJ_LINESEARCH_FAILED
+        assert ok.mean() > 0.99
+        assert np.all(cost[ok] < prev[ok])
+        np.testing.assert_array_equal(cost[-4:], cost[:4])
+        np.testing.assert_array_equal(s.get(_lib.K)[-4:], s.get(_lib.K)[:4])
+        for k, b in enumerate(spot):
+            rec = oracles[k].iterate(Ls[k])
+            Ls[k] = rec.L
+            assert abs(cost[b] - rec.L) <= 1e-8 * abs(rec.L)
+            assert s.get_int(_lib.I_LS_ITERS)[b] == rec.ls_iters
+            assert relerr(s.get(_lib.K)[b], oracles[k].K) < 1e-5
+        prev = cost
