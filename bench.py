@@ -252,9 +252,11 @@ def run_b200(args):
 
     # ------------------------------------------------------------------ device-resident timing
     fresh()
-    for _ in range(W):
+    cost_after = {}
+    for w in range(W):
         solver.iterate()
         gather_costs()
+        cost_after[w + 1] = float(solver.cost[0])
     it0 = solver.get_int(_lib.I_ITERS).astype(np.int64)
     launches0 = solver.launch_count()
     sampler = ClockSampler(local)
@@ -384,23 +386,27 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample of the same workload on the host cores (about 10-30 s of CPU work)
-            cpu_steps = 3
-            cv, procs, cdt, cunits = cpu_measure(args.horizon, cpu_steps, 1, per_proc=1)
+            cpu_steps = 6
+            cv, procs, cdt, cunits = cpu_measure(args.horizon, cpu_steps, 1, per_proc=2)
             line["cpu_baseline"] = {
                 "value": cv, "unit": UNIT, "cores": procs, "kind": "port",
-                "sample": f"{procs} trajectories (one per process, 1 thread each) x {cpu_steps} iLQR iterations of "
-                          f"the same C4 problem after 1 warm-up iteration ({cunits} trajectory-iterations in {cdt:.1f} s)"}
-            # cost vs reference: trajectory 0 re-solved by the oracle for the same W+K iterations
+                "sample": f"{2 * procs} trajectories (two per process, {procs} processes, 1 thread each) x {cpu_steps} "
+                          f"iLQR iterations of the same C4 problem after 1 warm-up iteration "
+                          f"({cunits} trajectory-iterations in {cdt:.1f} s wall)"}
+            # cost vs reference: trajectory 0 re-solved by the oracle.  Compared after 2 iterations:
+            # the N=200 open-loop-unstable contact problem amplifies a 1e-15 input perturbation to
+            # 1e-4 after four iterations in the oracle itself (DESIGN.md "Conditioning"), so longer
+            # horizons of iterations compare chaos, not implementations.
             from oracle.dynamics import HostDynamics
             from oracle.ilqr_port import IlqrOracle
             o = IlqrOracle(HostDynamics(prob.system), N, delta=prob.delta, beta=prob.beta, gamma=prob.gamma)
             o.set_initial_state(x0[0]); o.set_target_state(prob.x_nom)
             o.set_running_cost(prob.Q, prob.R); o.set_terminal_cost(prob.Qf); o.set_initial_guess(prob.u_guess)
             try:
-                o.solve(max_iters=W + K)
+                o.solve(max_iters=2)
                 Lo = o.trace[-1].L
-                line["cost_vs_oracle"] = {"trajectory": 0, "iterations": len(o.trace), "gpu": float(cost_dev[0]),
-                                          "oracle": Lo, "rel_err": abs(float(cost_dev[0]) - Lo) / abs(Lo)}
+                line["cost_vs_oracle"] = {"trajectory": 0, "iterations": 2, "gpu": cost_after[2],
+                                          "oracle": Lo, "rel_err": abs(cost_after[2] - Lo) / abs(Lo)}
             except RuntimeError as e:
                 line["cost_vs_oracle"] = {"error": str(e)}
         print(json.dumps(line))

@@ -3,6 +3,7 @@
 // here: every phase is a CUDA launch, and errors surface as negative status codes.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -10,6 +11,7 @@
 
 #include "../../include/ddp_b200.h"
 #include "kernels.cuh"
+#include "backward_mma.cuh"
 
 using namespace ddp;
 
@@ -34,6 +36,7 @@ struct ddp_solver {
   float ms[4];
   long long launches;
   bool timings_valid;
+  bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
   // array table
   double* darr[16];
   size_t dsize[16];
@@ -125,7 +128,26 @@ int launch_linearize(ddp_solver* s, const int* list, const int* count) {
   return 0;
 }
 template <class Model>
+int launch_backward_mma(ddp_solver* s) {
+  typedef BwdMmaCfg<Model::n, Model::m> C;
+  const size_t smem = sizeof(BwdMmaSmem<Model::n, Model::m>);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(backward_mma_kernel<Model>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_err = std::string("cudaFuncSetAttribute(backward_mma): ") + cudaGetErrorString(e);
+      return DDP_ERR_CUDA;
+    }
+    configured = true;
+  }
+  backward_mma_kernel<Model><<<s->d.B, C::NT, smem, s->stream>>>(s->d);
+  s->launches++;
+  return 0;
+}
+template <class Model>
 int launch_backward(ddp_solver* s) {
+  if (Model::n >= 16 && !s->scalar_backward) return launch_backward_mma<Model>(s);
   constexpr int NT = Cfg<Model>::BWD_THREADS;
   const size_t smem = sizeof(BwdSmem<Model::n, Model::m>);
   static bool configured = false;
@@ -343,6 +365,7 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   s->stream = (cudaStream_t)stream;
   s->launches = 0;
   s->timings_valid = false;
+  s->scalar_backward = getenv("DDP_SCALAR_BACKWARD") != nullptr;
   Dev& d = s->d;
   d.n = n; d.m = m; d.N = N; d.T = N - 1; d.B = B; d.A = A;
   Carver c{(char*)workspace_dev, 0};

@@ -288,5 +288,7 @@ def test_full_size_c4_properties():
             Ls[k] = rec.L
             assert abs(cost[b] - rec.L) <= 1e-8 * abs(rec.L)
             assert s.get_int(_lib.I_LS_ITERS)[b] == rec.ls_iters
-            assert relerr(s.get(_lib.K)[b], oracles[k].K) < 1e-5
+            # K at this size is ill-conditioned: perturbing x0 by 1e-15 moves the ORACLE's own K
+            # by ~7e-5 relative after one iteration (DESIGN.md "Conditioning"), so 1e-3 here.
+            assert relerr(s.get(_lib.K)[b], oracles[k].K) < 1e-3
         prev = cost
