@@ -89,6 +89,7 @@ void carve(Dev& d, double** params, int np, Carver& c) {
   d.acc = c.take<int>(B);
   d.iters = c.take<int>(B);
   d.counters = c.take<int>(4);
+  d.unres = c.take<int>(B);
   d.kplist = c.take<int>(B * T);
   d.kpcount = c.take<int>(B);
   d.seg_s = c.take<int>(B * T);
@@ -112,10 +113,10 @@ inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 // ---- templated launchers ---------------------------------------------------------------
 template <class Model>
-int launch_rollout(ddp_solver* s, int ls_base) {
+int launch_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
   constexpr int G = Cfg<Model>::G_ROLL;
-  const size_t threads = (size_t)s->d.B * s->d.A * G;
-  rollout_kernel<Model, G><<<cdiv(threads, 128), 128, 0, s->stream>>>(s->d, ls_base);
+  const size_t threads = (size_t)n_items * G;
+  rollout_kernel<Model, G><<<cdiv(threads, 128), 128, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
   s->launches++;
   return 0;
 }
@@ -165,8 +166,8 @@ int launch_backward(ddp_solver* s) {
   return 0;
 }
 
-int do_rollout(ddp_solver* s, int ls_base) {
-  DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base));
+int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
+  DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base, per_traj, n_items));
   return 0;
 }
 int do_linearize(ddp_solver* s, const int* list, const int* count) {
@@ -184,28 +185,35 @@ int do_backward(ddp_solver* s) {
     s->launches++;                                                            \
   } while (0)
 
-// _linesearch (ilqr.py:274-337) + commit (:375-376).  sync_rounds: keep launching rounds of A
-// candidates until every trajectory is resolved (one small D2H flag read per round).
+// _linesearch (ilqr.py:274-337) + commit (:375-376).  Round 0 evaluates the first A candidates of
+// every trajectory.  With sync_rounds, the trajectories that accepted none are compacted and
+// later rounds spread the whole candidate buffer (B*A slots) over them, so the usual case is
+// one or two rounds; each later round costs one small D2H counter read.
 int phase_linesearch(ddp_solver* s, bool sync_rounds) {
   Dev& d = s->d;
-  int ls_base = 0;
+  const int slots = d.B * d.A;
+  int ls_base = 0, per_traj = d.A, n_traj = d.B;
   while (true) {
-    int rc = do_rollout(s, ls_base);
+    int rc = do_rollout(s, ls_base, per_traj, n_traj * per_traj);
     if (rc) return rc;
-    LAUNCH1(pick_kernel, d, ls_base);
+    pick_kernel<<<cdiv(n_traj, 128), 128, 0, s->stream>>>(d, ls_base, per_traj, n_traj);
+    s->launches++;
     {
       dim3 grid(cdiv((size_t)d.N * d.n + (size_t)d.T * d.m, 256 * 4), d.B);
       commit_kernel<<<grid, 256, 0, s->stream>>>(d);
       s->launches++;
     }
     LAUNCH1(commit_done_kernel, d);
-    if (!sync_rounds) break;
+    ls_base += per_traj;
+    if (!sync_rounds || ls_base >= d.n_eps) break;
+    CK(cudaMemsetAsync(d.counters, 0, sizeof(int), s->stream));
+    LAUNCH1(unresolved_kernel, d);
     CK(cudaMemcpyAsync(s->h_counters, d.counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    if (s->h_counters[0] == 0) break;
-    CK(cudaMemsetAsync(d.counters, 0, sizeof(int), s->stream));
-    ls_base += d.A;
-    if (ls_base >= d.n_eps) break;
+    n_traj = s->h_counters[0];
+    if (n_traj == 0) break;
+    per_traj = slots / n_traj;
+    if (per_traj > d.n_eps - ls_base) per_traj = d.n_eps - ls_base;
   }
   return 0;
 }

@@ -22,7 +22,7 @@ struct Dev {
   double *x_bar, *u_bar, *K, *kappa, *dV, *fx, *fu;
   double *xc, *uc, *Lc, *Ec;
   double *L, *L_new, *eps, *improvement;
-  int *ls_iters, *status, *active, *resolved, *acc, *iters, *counters;
+  int *ls_iters, *status, *active, *resolved, *acc, *iters, *counters, *unres;
   // keypoints
   int kp_method, minN, maxN;
   double jerk_thr, err_thr;
@@ -56,14 +56,24 @@ __device__ __forceinline__ unsigned group_mask(int G) {
 // are evaluated redundantly by each lane (identical values, so control flow stays uniform).
 // =============================================================================================
 template <class Model, int G>
-__global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base) {
+__global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   constexpr int n = Model::n, m = Model::m;
   constexpr int RPL = (m + G - 1) / G;  // feedback rows per lane
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int item = gtid / G, lane = gtid % G;
-  if (item >= d.B * d.A) return;
-  const int b = item / d.A, ai = item % d.A;
-  if (!d.active[b] || d.resolved[b]) return;
+  // work item -> (trajectory b, candidate c).  Round 0: every trajectory, candidates
+  // [0, A): item = b*A + ai.  Later rounds: only the trajectories still unresolved (compacted
+  // in d.unres), per_traj candidates each starting at ls_base; the slot index is the item.
+  if (item >= n_items) return;
+  int b, ai;
+  if (ls_base == 0) {
+    b = item / per_traj;
+    ai = item % per_traj;
+    if (!d.active[b] || d.resolved[b]) return;
+  } else {
+    b = d.unres[item / per_traj];
+    ai = item % per_traj;
+  }
   const int c = ls_base + ai;
   if (c >= d.n_eps) {
     if (lane == 0) {
@@ -119,7 +129,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base) {
       else u[r] = __shfl_sync(mask, mine[r / G], gbase + (r % G));
     }
     // x_{t+1} = f(x_t, u_t)                                          (ilqr.py:316)
-    Model::template step<double>(x, u, xn, d.params);
+    if constexpr (Model::COOP == G && G > 1) Model::step_coop(lane, mask, gbase, x, u, xn, d.params);
+    else Model::template step<double>(x, u, xn, d.params);
     bool fin = true;
 #pragma unroll
     for (int j = 0; j < n; ++j) fin = fin && isfinite(xn[j]);
@@ -200,18 +211,20 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base) {
 // =============================================================================================
 // K2  first-satisfying pick (ilqr.py:329-337) over the A candidates of this round.
 // =============================================================================================
-__global__ void pick_kernel(Dev d, int ls_base) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= d.B) return;
-  if (!d.active[b] || d.resolved[b]) return;
+__global__ void pick_kernel(Dev d, int ls_base, int per_traj, int n_traj) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_traj) return;
+  const int b = (ls_base == 0) ? j : d.unres[j];
+  if (ls_base == 0 && (!d.active[b] || d.resolved[b])) return;
   const double Llast = d.L[b];
-  for (int ai = 0; ai < d.A; ++ai) {
+  for (int ai = 0; ai < per_traj; ++ai) {
     const int c = ls_base + ai;
     if (c >= d.n_eps) break;
-    const double Lcand = d.Lc[(size_t)b * d.A + ai];
+    const size_t slot = (size_t)j * per_traj + ai;
+    const double Lcand = d.Lc[slot];
     const double improvement = Llast - Lcand;
-    if (improvement > d.gamma * d.Ec[(size_t)b * d.A + ai]) {
-      d.acc[b] = ai;
+    if (improvement > d.gamma * d.Ec[slot]) {
+      d.acc[b] = (int)slot;
       d.resolved[b] = 1;
       d.eps[b] = d.eps_table[c];
       d.ls_iters[b] = c + 1;
@@ -220,25 +233,30 @@ __global__ void pick_kernel(Dev d, int ls_base) {
     }
   }
   d.acc[b] = -1;
-  if (ls_base + d.A >= d.n_eps) {  // eps < 1e-8: RuntimeError("linesearch failed ...")  (:337)
+  if (ls_base + per_traj >= d.n_eps) {  // eps < 1e-8: RuntimeError("linesearch failed ...")  (:337)
     d.status[b] = 2;
     d.active[b] = 0;
     d.resolved[b] = 1;
     d.ls_iters[b] = d.n_eps;
-  } else {
-    atomicAdd(&d.counters[0], 1);
   }
+}
+// compact the trajectories that are still unresolved into d.unres (order is irrelevant:
+// candidates are independent), count in counters[0]
+__global__ void unresolved_kernel(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  if (d.active[b] && !d.resolved[b]) d.unres[atomicAdd(&d.counters[0], 1)] = b;
 }
 
 // u_bar <- u, x_bar <- x of the accepted candidate (ilqr.py:375-376).
 __global__ void commit_kernel(Dev d) {
   const int b = blockIdx.y;
   if (!d.active[b]) return;
-  const int ai = d.acc[b];
-  if (ai < 0) return;
+  const int slot = d.acc[b];
+  if (slot < 0) return;
   const size_t nx = (size_t)d.N * d.n, nu = (size_t)d.T * d.m;
-  const double* xs = d.xc + ((size_t)b * d.A + ai) * nx;
-  const double* us = d.uc + ((size_t)b * d.A + ai) * nu;
+  const double* xs = d.xc + (size_t)slot * nx;
+  const double* us = d.uc + (size_t)slot * nu;
   double* xd = d.x_bar + (size_t)b * nx;
   double* ud = d.u_bar + (size_t)b * nu;
   for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nx + nu; i += (size_t)gridDim.x * blockDim.x) {
@@ -524,52 +542,60 @@ struct BwdSmem {
   double Qu[m], g[m], kap[m], ub[m];
 };
 
-// explicit inverse of the m x m matrix A (destroyed) into Inv by Gauss-Jordan with partial
-// pivoting; one warp, lane r owns row r.  Stands in for np.linalg.inv(Quu) (ilqr.py:655).
+// explicit inverse of the m x m matrix A into Inv by Gauss-Jordan with partial pivoting; one
+// warp, lane r keeps row r of [A | I] in registers, the pivot row is broadcast with shuffles,
+// rows are never physically swapped (the pivot lane of column c is remembered and the rows are
+// gathered at the end).  Stands in for np.linalg.inv(Quu) (ilqr.py:655).  m <= 32.
 template <int m>
-__device__ void invert_warp(double* A, double* Inv) {
+__device__ void invert_warp(const double* A, double* Inv) {
   const int lane = threadIdx.x & 31;
-  for (int i = lane; i < m * m; i += 32) Inv[i] = (i / m == i % m) ? 1.0 : 0.0;
-  __syncwarp();
+  const unsigned full = 0xffffffffu;
+  double a[m], v[m];
+#pragma unroll
+  for (int j = 0; j < m; ++j) {
+    a[j] = (lane < m) ? A[lane * m + j] : 0.0;
+    v[j] = (lane == j) ? 1.0 : 0.0;
+  }
+  bool used = (lane >= m);  // lanes that may no longer serve as pivot rows
+  int mycol = -1;           // pivot column this lane's row was used for
+#pragma unroll
   for (int c = 0; c < m; ++c) {
-    // pivot search over rows >= c
-    double best = (lane >= c && lane < m) ? fabs(A[lane * m + c]) : -1.0;
+    double best = used ? -1.0 : fabs(a[c]);
     int arg = lane;
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      const double ob = __shfl_xor_sync(full, best, o);
+      const int oa = __shfl_xor_sync(full, arg, o);
       if (ob > best || (ob == best && oa < arg)) {
         best = ob;
         arg = oa;
       }
     }
-    if (arg != c) {
-      for (int j = lane; j < m; j += 32) {
-        double tmp = A[c * m + j];
-        A[c * m + j] = A[arg * m + j];
-        A[arg * m + j] = tmp;
-        tmp = Inv[c * m + j];
-        Inv[c * m + j] = Inv[arg * m + j];
-        Inv[arg * m + j] = tmp;
+    const double piv = 1.0 / __shfl_sync(full, a[c], arg);
+    const double f = (lane == arg) ? 0.0 : a[c];
+    if (lane == arg) {
+      used = true;
+      mycol = c;
+    }
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+      const double pa = __shfl_sync(full, a[j], arg) * piv;
+      const double pv = __shfl_sync(full, v[j], arg) * piv;
+      if (lane == arg) {
+        a[j] = pa;
+        v[j] = pv;
+      } else {
+        a[j] = fma(-f, pa, a[j]);
+        v[j] = fma(-f, pv, v[j]);
       }
     }
-    __syncwarp();
-    const double piv = 1.0 / A[c * m + c];
-    __syncwarp();
-    for (int j = lane; j < m; j += 32) {
-      A[c * m + j] *= piv;
-      Inv[c * m + j] *= piv;
-    }
-    __syncwarp();
-    if (lane < m && lane != c) {
-      const double f = A[lane * m + c];
-      for (int j = 0; j < m; ++j) {
-        A[lane * m + j] = fma(-f, A[c * m + j], A[lane * m + j]);
-        Inv[lane * m + j] = fma(-f, Inv[c * m + j], Inv[lane * m + j]);
-      }
-    }
-    __syncwarp();
   }
+  // row c of the inverse is the row held by the lane that pivoted column c
+  if (mycol >= 0) {
+#pragma unroll
+    for (int j = 0; j < m; ++j) Inv[mycol * m + j] = v[j];
+  }
+  __syncwarp();
 }
 
 template <class Model, int NT>

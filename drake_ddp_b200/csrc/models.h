@@ -35,6 +35,7 @@ enum ModelId {
 // p = [dt, mass, length, damping, g]
 struct Pendulum {
   static constexpr int n = 2, m = 1, np = 5;
+  static constexpr int COOP = 1;
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const double h = p[0], ml2 = p[1] * p[2] * p[2], mgl = p[1] * p[4] * p[2];
@@ -52,6 +53,7 @@ struct Pendulum {
 // p = [dt, m1, m2, l1, lc1, lc2, Ic1, Ic2, b1, b2, g]
 struct Acrobot {
   static constexpr int n = 4, m = 1, np = 11;
+  static constexpr int COOP = 1;
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const double h = p[0], m1 = p[1], m2 = p[2], l1 = p[3], lc1 = p[4], lc2 = p[5];
@@ -90,6 +92,7 @@ struct Acrobot {
 template <bool WALL>
 struct CartPoleT {
   static constexpr int n = 4, m = 1, np = 9;
+  static constexpr int COOP = 1;
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const double mc = p[1], mp = p[2], l = p[3], g = p[4];
@@ -155,14 +158,115 @@ DDP_HD S sphere_plane_force(const S& depth, double R, double E) {
 //      l_abad, l_thigh, l_shank, hip_x, hip_y, foot_radius, E, mu, v_stiction, g]
 struct Quadruped {
   static constexpr int n = 36, m = 12, np = 20;
+  static constexpr int COOP = 4;  // step_coop: one leg per lane of a 4-lane group
+
+  template <class S>
+  struct LegOut {
+    S Fx, Fy, Fz;  // world force on the body
+    S Tx, Ty, Tz;  // body-frame torque on the body
+    S a0, a1, a2;  // joint accelerations (abad, hip, knee)
+  };
+  template <class S>
+  struct BasePose {
+    S R00, R01, R02, R10, R11, R12, R20, R21, R22, sr, cr, sp, cp;
+  };
+  template <class S>
+  DDP_HD static void base_pose(const S* q, BasePose<S>& B) {
+    S sy, cy;
+    sincos_(q[3], &B.sr, &B.cr);
+    sincos_(q[4], &B.sp, &B.cp);
+    sincos_(q[5], &sy, &cy);
+    // R = Rz(yaw) Ry(pitch) Rx(roll), body -> world
+    B.R00 = cy * B.cp; B.R01 = cy * B.sp * B.sr - sy * B.cr; B.R02 = cy * B.sp * B.cr + sy * B.sr;
+    B.R10 = sy * B.cp; B.R11 = sy * B.sp * B.sr + cy * B.cr; B.R12 = sy * B.sp * B.cr - cy * B.sr;
+    B.R20 = -B.sp; B.R21 = B.cp * B.sr; B.R22 = B.cp * B.cr;
+  }
+  // One leg: foot kinematics, compliant ground contact, joint accelerations.
+  // sx = +1 front / -1 hind, sd = +1 left / -1 right; (qa,qh,qk) joint angles, (va,vh,vk) rates.
+  template <class S>
+  DDP_HD static void leg(double sx, double sd, const S& qa, const S& qh, const S& qk, const S& va,
+                         const S& vh, const S& vk, const S& ua, const S& uh, const S& uk, const S& pz,
+                         const S* v, const BasePose<S>& B, const double* p, LegOut<S>& o) {
+    const double bj = p[9], l1 = p[10], l2 = p[11], l3 = p[12];
+    const double hx = p[13], hy = p[14], rf = p[15], E = p[16], mu = p[17], vs = p[18];
+    S sa, ca, sh, ch, sk, ck;
+    sincos_(qa, &sa, &ca);
+    sincos_(qh, &sh, &ch);
+    sincos_(qh + qk, &sk, &ck);
+    const double ly = sd * l1;
+    S lx = -(l2 * sh) - l3 * sk;
+    S lz = -(l2 * ch) - l3 * ck;
+    // foot in body frame and its joint Jacobian (columns: abad, hip, knee)
+    S rx = hx * sx + lx;
+    S ry = hy * sd + (ly * ca - lz * sa);
+    S rz = ly * sa + lz * ca;
+    S J01 = lz, J02 = -(l3 * ck);
+    S J10 = -(ly * sa) - lz * ca, J11 = lx * sa, J12 = -(l3 * sk) * sa;
+    S J20 = ly * ca - lz * sa, J21 = -(lx * ca), J22 = (l3 * sk) * ca;
+    S cz = pz + B.R20 * rx + B.R21 * ry + B.R22 * rz;
+    S depth = rf - cz;
+    S tau0 = S(0.0), tau1 = S(0.0), tau2 = S(0.0);
+    o.Fx = S(0.0); o.Fy = S(0.0); o.Fz = S(0.0);
+    o.Tx = S(0.0); o.Ty = S(0.0); o.Tz = S(0.0);
+    if (val(depth) > 0.0) {
+      // body-frame foot velocity relative to the body origin: w x r + J qd
+      S bx = v[4] * rz - v[5] * ry + J01 * vh + J02 * vk;
+      S by = v[5] * rx - v[3] * rz + J10 * va + J11 * vh + J12 * vk;
+      S bz = v[3] * ry - v[4] * rx + J20 * va + J21 * vh + J22 * vk;
+      S wx = v[0] + B.R00 * bx + B.R01 * by + B.R02 * bz;
+      S wy = v[1] + B.R10 * bx + B.R11 * by + B.R12 * bz;
+      S Fn = sphere_plane_force(depth, rf, E);
+      S sl = sqrt_(wx * wx + wy * wy + vs * vs);
+      S ftx = -(mu * Fn) * wx / sl;
+      S fty = -(mu * Fn) * wy / sl;
+      o.Fx = ftx; o.Fy = fty; o.Fz = Fn;
+      S fbx = B.R00 * ftx + B.R10 * fty + B.R20 * Fn;   // force in body frame
+      S fby = B.R01 * ftx + B.R11 * fty + B.R21 * Fn;
+      S fbz = B.R02 * ftx + B.R12 * fty + B.R22 * Fn;
+      o.Tx = ry * fbz - rz * fby;
+      o.Ty = rz * fbx - rx * fbz;
+      o.Tz = rx * fby - ry * fbx;
+      tau0 = J10 * fby + J20 * fbz;
+      tau1 = J01 * fbx + J11 * fby + J21 * fbz;
+      tau2 = J02 * fbx + J12 * fby + J22 * fbz;
+    }
+    o.a0 = (ua + tau0 - bj * va) / p[6];
+    o.a1 = (uh + tau1 - bj * vh) / p[7];
+    o.a2 = (uk + tau2 - bj * vk) / p[8];
+  }
+  // base accelerations from the summed leg loads, then the semi-implicit Euler update
+  template <class S>
+  DDP_HD static void integrate(S* q, S* v, const S* acc, const BasePose<S>& B, double h) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) v[i] = v[i] + h * acc[i];
+    // q+ = q + h N(q) v+   (ZYX Euler rates from body angular velocity)
+    q[0] = q[0] + h * v[0];
+    q[1] = q[1] + h * v[1];
+    q[2] = q[2] + h * v[2];
+    S tp = B.sp / B.cp;
+    S wyz = B.sr * v[4] + B.cr * v[5];
+    q[3] = q[3] + h * (v[3] + tp * wyz);
+    q[4] = q[4] + h * (B.cr * v[4] - B.sr * v[5]);
+    q[5] = q[5] + h * (wyz / B.cp);
+#pragma unroll
+    for (int i = 6; i < 18; ++i) q[i] = q[i] + h * v[i];
+  }
+  template <class S>
+  DDP_HD static void base_acc(const S& Fx, const S& Fy, const S& Fz, const S& Tx, const S& Ty, const S& Tz,
+                              const S* v, const double* p, S* acc) {
+    const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5], g = p[19];
+    acc[0] = Fx / mass;
+    acc[1] = Fy / mass;
+    acc[2] = Fz / mass - g;
+    acc[3] = (Tx - (Iz - Iy) * v[4] * v[5]) / Ix;
+    acc[4] = (Ty - (Ix - Iz) * v[5] * v[3]) / Iy;
+    acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) / Iz;
+  }
+
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const int sub = (int)p[1];
     const double h = p[0] / sub;
-    const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5];
-    const double bj = p[9], l1 = p[10], l2 = p[11], l3 = p[12];
-    const double hx = p[13], hy = p[14], rf = p[15], E = p[16], mu = p[17], vs = p[18];
-    const double g = p[19];
     S q[18], v[18];
 #pragma unroll
     for (int i = 0; i < 18; ++i) {
@@ -170,89 +274,25 @@ struct Quadruped {
       v[i] = x[18 + i];
     }
     for (int it = 0; it < sub; ++it) {
-      S sr, cr, sp, cp, sy, cy;
-      sincos_(q[3], &sr, &cr);
-      sincos_(q[4], &sp, &cp);
-      sincos_(q[5], &sy, &cy);
-      // R = Rz(yaw) Ry(pitch) Rx(roll), body -> world
-      S R00 = cy * cp, R01 = cy * sp * sr - sy * cr, R02 = cy * sp * cr + sy * sr;
-      S R10 = sy * cp, R11 = sy * sp * sr + cy * cr, R12 = sy * sp * cr - cy * sr;
-      S R20 = -sp, R21 = cp * sr, R22 = cp * cr;
-      S Fx = 0.0 * q[0], Fy = Fx, Fz = Fx;  // world force on the body
-      S Tx = Fx, Ty = Fx, Tz = Fx;          // body-frame torque on the body
+      BasePose<S> B;
+      base_pose(q, B);
+      LegOut<S> o[4];
       S acc[18];
 #pragma unroll
-      for (int leg = 0; leg < 4; ++leg) {
-        const double sx = (leg < 2) ? 1.0 : -1.0;
-        const double sd = (leg & 1) ? 1.0 : -1.0;
-        const S* ql = q + 6 + 3 * leg;
-        const S* vl = v + 6 + 3 * leg;
-        S sa, ca, sh, ch, sk, ck;
-        sincos_(ql[0], &sa, &ca);
-        sincos_(ql[1], &sh, &ch);
-        sincos_(ql[1] + ql[2], &sk, &ck);
-        const double ly = sd * l1;
-        S lx = -(l2 * sh) - l3 * sk;
-        S lz = -(l2 * ch) - l3 * ck;
-        // foot in body frame and its joint Jacobian (columns: abad, hip, knee)
-        S rx = hx * sx + lx;
-        S ry = hy * sd + (ly * ca - lz * sa);
-        S rz = ly * sa + lz * ca;
-        S J01 = lz, J02 = -(l3 * ck);
-        S J10 = -(ly * sa) - lz * ca, J11 = lx * sa, J12 = -(l3 * sk) * sa;
-        S J20 = ly * ca - lz * sa, J21 = -(lx * ca), J22 = (l3 * sk) * ca;
-        // foot height and world velocity
-        S cz = q[2] + R20 * rx + R21 * ry + R22 * rz;
-        S depth = rf - cz;
-        S tau0 = 0.0 * depth, tau1 = tau0, tau2 = tau0;
-        if (val(depth) > 0.0) {
-          // body-frame foot velocity relative to body origin: w x r + J qd
-          S bx = v[4] * rz - v[5] * ry + J01 * vl[1] + J02 * vl[2];
-          S by = v[5] * rx - v[3] * rz + J10 * vl[0] + J11 * vl[1] + J12 * vl[2];
-          S bz = v[3] * ry - v[4] * rx + J20 * vl[0] + J21 * vl[1] + J22 * vl[2];
-          S wx = v[0] + R00 * bx + R01 * by + R02 * bz;
-          S wy = v[1] + R10 * bx + R11 * by + R12 * bz;
-          S Fn = sphere_plane_force(depth, rf, E);
-          S sl = sqrt_(wx * wx + wy * wy + vs * vs);
-          S ftx = -(mu * Fn) * wx / sl;
-          S fty = -(mu * Fn) * wy / sl;
-          Fx = Fx + ftx;
-          Fy = Fy + fty;
-          Fz = Fz + Fn;
-          // force in body frame
-          S fbx = R00 * ftx + R10 * fty + R20 * Fn;
-          S fby = R01 * ftx + R11 * fty + R21 * Fn;
-          S fbz = R02 * ftx + R12 * fty + R22 * Fn;
-          Tx = Tx + (ry * fbz - rz * fby);
-          Ty = Ty + (rz * fbx - rx * fbz);
-          Tz = Tz + (rx * fby - ry * fbx);
-          tau0 = J10 * fby + J20 * fbz;
-          tau1 = J01 * fbx + J11 * fby + J21 * fbz;
-          tau2 = J02 * fbx + J12 * fby + J22 * fbz;
-        }
-        acc[6 + 3 * leg + 0] = (u[3 * leg + 0] + tau0 - bj * vl[0]) / p[6];
-        acc[6 + 3 * leg + 1] = (u[3 * leg + 1] + tau1 - bj * vl[1]) / p[7];
-        acc[6 + 3 * leg + 2] = (u[3 * leg + 2] + tau2 - bj * vl[2]) / p[8];
+      for (int l = 0; l < 4; ++l) {
+        leg((l < 2) ? 1.0 : -1.0, (l & 1) ? 1.0 : -1.0, q[6 + 3 * l], q[7 + 3 * l], q[8 + 3 * l],
+            v[6 + 3 * l], v[7 + 3 * l], v[8 + 3 * l], u[3 * l], u[3 * l + 1], u[3 * l + 2], q[2], v, B, p,
+            o[l]);
+        acc[6 + 3 * l] = o[l].a0;
+        acc[7 + 3 * l] = o[l].a1;
+        acc[8 + 3 * l] = o[l].a2;
       }
-      acc[0] = Fx / mass;
-      acc[1] = Fy / mass;
-      acc[2] = Fz / mass - g;
-      acc[3] = (Tx - (Iz - Iy) * v[4] * v[5]) / Ix;
-      acc[4] = (Ty - (Ix - Iz) * v[5] * v[3]) / Iy;
-      acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) / Iz;
-#pragma unroll
-      for (int i = 0; i < 18; ++i) v[i] = v[i] + h * acc[i];
-      // q+ = q + h N(q) v+   (ZYX Euler rates from body angular velocity)
-      q[0] = q[0] + h * v[0];
-      q[1] = q[1] + h * v[1];
-      q[2] = q[2] + h * v[2];
-      S tp = sp / cp;
-      S wyz = sr * v[4] + cr * v[5];
-      q[3] = q[3] + h * (v[3] + tp * wyz);
-      q[4] = q[4] + h * (cr * v[4] - sr * v[5]);
-      q[5] = q[5] + h * (wyz / cp);
-#pragma unroll
-      for (int i = 6; i < 18; ++i) q[i] = q[i] + h * v[i];
+      // pairwise sums (same association as the 4-lane butterfly in step_coop)
+      base_acc((o[0].Fx + o[1].Fx) + (o[2].Fx + o[3].Fx), (o[0].Fy + o[1].Fy) + (o[2].Fy + o[3].Fy),
+               (o[0].Fz + o[1].Fz) + (o[2].Fz + o[3].Fz), (o[0].Tx + o[1].Tx) + (o[2].Tx + o[3].Tx),
+               (o[0].Ty + o[1].Ty) + (o[2].Ty + o[3].Ty), (o[0].Tz + o[1].Tz) + (o[2].Tz + o[3].Tz), v, p,
+               acc);
+      integrate(q, v, acc, B, h);
     }
 #pragma unroll
     for (int i = 0; i < 18; ++i) {
@@ -260,6 +300,59 @@ struct Quadruped {
       xn[18 + i] = v[i];
     }
   }
+
+#if defined(__CUDACC__)
+  // Same map evaluated by a 4-lane group: lane l computes leg l, loads are combined with a
+  // two-stage butterfly, joint accelerations are exchanged with shuffles.  Bit-identical to
+  // step<double>() (same operations, same association of the sums).
+  __device__ __forceinline__ static double pick4(int l, double a, double b, double c, double d) {
+    return l == 0 ? a : (l == 1 ? b : (l == 2 ? c : d));
+  }
+  __device__ __forceinline__ static void step_coop(int lane, unsigned mask, int gbase, const double* x,
+                                                   const double* u, double* xn, const double* p) {
+    const int sub = (int)p[1];
+    const double h = p[0] / sub;
+    double q[18], v[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      q[i] = x[i];
+      v[i] = x[18 + i];
+    }
+    const double ua = pick4(lane, u[0], u[3], u[6], u[9]);
+    const double uh = pick4(lane, u[1], u[4], u[7], u[10]);
+    const double uk = pick4(lane, u[2], u[5], u[8], u[11]);
+    const double sx = (lane < 2) ? 1.0 : -1.0, sd = (lane & 1) ? 1.0 : -1.0;
+    for (int it = 0; it < sub; ++it) {
+      BasePose<double> B;
+      base_pose(q, B);
+      LegOut<double> o;
+      leg(sx, sd, pick4(lane, q[6], q[9], q[12], q[15]), pick4(lane, q[7], q[10], q[13], q[16]),
+          pick4(lane, q[8], q[11], q[14], q[17]), pick4(lane, v[6], v[9], v[12], v[15]),
+          pick4(lane, v[7], v[10], v[13], v[16]), pick4(lane, v[8], v[11], v[14], v[17]), ua, uh, uk, q[2],
+          v, B, p, o);
+      double f[6] = {o.Fx, o.Fy, o.Fz, o.Tx, o.Ty, o.Tz};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        f[k] += __shfl_xor_sync(mask, f[k], 1);
+        f[k] += __shfl_xor_sync(mask, f[k], 2);
+      }
+      double acc[18];
+      base_acc(f[0], f[1], f[2], f[3], f[4], f[5], v, p, acc);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        acc[6 + 3 * l] = __shfl_sync(mask, o.a0, gbase + l);
+        acc[7 + 3 * l] = __shfl_sync(mask, o.a1, gbase + l);
+        acc[8 + 3 * l] = __shfl_sync(mask, o.a2, gbase + l);
+      }
+      integrate(q, v, acc, B, h);
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      xn[i] = q[i];
+      xn[18 + i] = v[i];
+    }
+  }
+#endif
 };
 
 // ------------------------------------------------------------------------------
@@ -274,6 +367,7 @@ struct Quadruped {
 //      E, mu, v_stiction, g, base_z]
 struct ArmBall {
   static constexpr int n = 27, m = 7, np = 19;
+  static constexpr int COOP = 1;
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const int sub = (int)p[1];
@@ -421,6 +515,7 @@ struct ArmBall {
 template <int N_, int M_>
 struct AffineSin {
   static constexpr int n = N_, m = M_, np = 1 + N_ * N_ + N_ * M_;
+  static constexpr int COOP = 1;
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const double* A = p + 1;

