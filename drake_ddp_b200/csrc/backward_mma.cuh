@@ -83,7 +83,7 @@ struct BwdMmaSmem {
 };
 
 template <class Model>
-__global__ void __launch_bounds__(BwdMmaCfg<Model::n, Model::m>::NT)
+__global__ void __launch_bounds__(BwdMmaCfg<Model::n, Model::m>::NT, 3)
 backward_mma_kernel(Dev d) {
   constexpr int n = Model::n, m = Model::m;
   typedef BwdMmaCfg<n, m> C;
@@ -157,25 +157,9 @@ backward_mma_kernel(Dev d) {
     const double* Fx = s.Fx[buf];
     const double* Fu = s.Fu[buf];
 
-    // ---------------- phase 1: W = Vxx fx, Wu = Vxx fu ; Qx, Qu ---------------------------
+    // ---------------- phase 1: Wu = Vxx fu ; last warp: Qx, Qu ----------------------------------
     if (warp < TN) {
       const int w = warp;
-      double acc[TN][2];
-#pragma unroll
-      for (int i = 0; i < TN; ++i) acc[i][0] = acc[i][1] = 0.0;
-#pragma unroll
-      for (int kk = 0; kk < KN; ++kk) {
-        const int k = 4 * kk + tg;
-        const double bf = ldz(Fx, n, k, 8 * w + g, n, n);
-#pragma unroll
-        for (int mt = 0; mt < TN; ++mt) dmma(acc[mt], ldz(s.Vxx, n, 8 * mt + g, k, n, n), bf);
-      }
-#pragma unroll
-      for (int mt = 0; mt < TN; ++mt) {
-        const int r = 8 * mt + g, c = 8 * w + 2 * tg;
-        if (r < n && c < n) s.W[r * n + c] = acc[mt][0];
-        if (r < n && c + 1 < n) s.W[r * n + c + 1] = acc[mt][1];
-      }
       double accu[TM][2];
 #pragma unroll
       for (int i = 0; i < TM; ++i) accu[i][0] = accu[i][1] = 0.0;
@@ -207,24 +191,56 @@ backward_mma_kernel(Dev d) {
             c = fma(2.0 * xnom[j], Q[j * n + k], c);
           }
         }
-        double q = a - c;
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) q = fma(Fx[i * n + k], s.Vx[i], q);
-        s.Qx[k] = q;
+        double q0 = a - c, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+        int i = 0;
+        for (; i + 3 < n; i += 4) {
+          q0 = fma(Fx[i * n + k], s.Vx[i], q0);
+          q1 = fma(Fx[(i + 1) * n + k], s.Vx[i + 1], q1);
+          q2 = fma(Fx[(i + 2) * n + k], s.Vx[i + 2], q2);
+          q3 = fma(Fx[(i + 3) * n + k], s.Vx[i + 3], q3);
+        }
+        for (; i < n; ++i) q0 = fma(Fx[i * n + k], s.Vx[i], q0);
+        s.Qx[k] = (q0 + q1) + (q2 + q3);
       }
       for (int r = lane; r < m; r += 32) {
         double a = 0.0;
         for (int j = 0; j < m; ++j) a = fma(2.0 * R[r * m + j], ub[j], a);
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) a = fma(Fu[i * m + r], s.Vx[i], a);
-        s.Qu[r] = a;
+        double q1 = 0.0;
+        int i = 0;
+        for (; i + 1 < n; i += 2) {
+          a = fma(Fu[i * m + r], s.Vx[i], a);
+          q1 = fma(Fu[(i + 1) * m + r], s.Vx[i + 1], q1);
+        }
+        for (; i < n; ++i) a = fma(Fu[i * m + r], s.Vx[i], a);
+        s.Qu[r] = a + q1;
       }
     }
     __syncthreads();
 
-    // ---------------- phase 2: Qxx (into Vxx), Qux ; last warp: Quu, inverse, kappa, g -------
+    // ---------------- phase 2: strips: W = Vxx fx, then Qxx (into Vxx) and Qux ------------------
+    // ---------------- meanwhile the last warp: Quu, its inverse, kappa, g -----------------------
     if (warp < TN) {
       const int w = warp;
+      {
+        double acc[TN][2];
+#pragma unroll
+        for (int i = 0; i < TN; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KN; ++kk) {
+          const int k = 4 * kk + tg;
+          const double bf = ldz(Fx, n, k, 8 * w + g, n, n);
+#pragma unroll
+          for (int mt = 0; mt < TN; ++mt) dmma(acc[mt], ldz(s.Vxx, n, 8 * mt + g, k, n, n), bf);
+        }
+#pragma unroll
+        for (int mt = 0; mt < TN; ++mt) {
+          const int r = 8 * mt + g, c = 8 * w + 2 * tg;
+          if (r < n && c < n) s.W[r * n + c] = acc[mt][0];
+          if (r < n && c + 1 < n) s.W[r * n + c + 1] = acc[mt][1];
+        }
+      }
+      // all strips of W written and all reads of the old Vxx done (strip warps only)
+      asm volatile("bar.sync 1, %0;" ::"r"(TN * 32) : "memory");
       double aq[TN][2], au[TM][2];
 #pragma unroll
       for (int i = 0; i < TN; ++i) aq[i][0] = aq[i][1] = 0.0;

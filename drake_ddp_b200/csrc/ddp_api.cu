@@ -148,7 +148,9 @@ int launch_backward_mma(ddp_solver* s) {
 }
 template <class Model>
 int launch_backward(ddp_solver* s) {
-  if (Model::n >= 16 && !s->scalar_backward) return launch_backward_mma<Model>(s);
+  if constexpr (Model::n >= 16) {
+    if (!s->scalar_backward) return launch_backward_mma<Model>(s);
+  }
   constexpr int NT = Cfg<Model>::BWD_THREADS;
   const size_t smem = sizeof(BwdSmem<Model::n, Model::m>);
   static bool configured = false;

@@ -542,58 +542,48 @@ struct BwdSmem {
   double Qu[m], g[m], kap[m], ub[m];
 };
 
-// explicit inverse of the m x m matrix A into Inv by Gauss-Jordan with partial pivoting; one
-// warp, lane r keeps row r of [A | I] in registers, the pivot row is broadcast with shuffles,
-// rows are never physically swapped (the pivot lane of column c is remembered and the rows are
-// gathered at the end).  Stands in for np.linalg.inv(Quu) (ilqr.py:655).  m <= 32.
+// explicit inverse of the m x m matrix A into Inv: in-place Gauss-Jordan with partial pivoting,
+// one warp, lane r keeps row r in registers.  Rows are never physically swapped: the pivot lane
+// of every column is remembered and the permutation is undone when the result is stored.  The
+// pivot search is two REDUX max ops on the IEEE bit pattern of |a| plus a ballot (lowest lane
+// wins ties); the pivot row is broadcast with shuffles.  Stands in for np.linalg.inv(Quu)
+// (ilqr.py:655).  m <= 32.
 template <int m>
 __device__ void invert_warp(const double* A, double* Inv) {
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
-  double a[m], v[m];
+  double a[m];
 #pragma unroll
-  for (int j = 0; j < m; ++j) {
-    a[j] = (lane < m) ? A[lane * m + j] : 0.0;
-    v[j] = (lane == j) ? 1.0 : 0.0;
-  }
+  for (int j = 0; j < m; ++j) a[j] = (lane < m) ? A[lane * m + j] : 0.0;
   bool used = (lane >= m);  // lanes that may no longer serve as pivot rows
   int mycol = -1;           // pivot column this lane's row was used for
+  int rc[m];                // pivot lane of each column (warp-uniform)
 #pragma unroll
   for (int c = 0; c < m; ++c) {
-    double best = used ? -1.0 : fabs(a[c]);
-    int arg = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(full, best, o);
-      const int oa = __shfl_xor_sync(full, arg, o);
-      if (ob > best || (ob == best && oa < arg)) {
-        best = ob;
-        arg = oa;
-      }
-    }
-    const double piv = 1.0 / __shfl_sync(full, a[c], arg);
-    const double f = (lane == arg) ? 0.0 : a[c];
-    if (lane == arg) {
+    const unsigned long long key = used ? 0ull : (unsigned long long)__double_as_longlong(fabs(a[c])) + 1ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(full, hi);
+    const unsigned ml = __reduce_max_sync(full, hi == mh ? lo : 0u);
+    const int arg = __ffs(__ballot_sync(full, hi == mh && lo == ml)) - 1;
+    rc[c] = arg;
+    const bool isp = (lane == arg);
+    if (isp) {
       used = true;
       mycol = c;
     }
+    const double piv = 1.0 / __shfl_sync(full, a[c], arg);
+    const double f = a[c];
 #pragma unroll
     for (int j = 0; j < m; ++j) {
-      const double pa = __shfl_sync(full, a[j], arg) * piv;
-      const double pv = __shfl_sync(full, v[j], arg) * piv;
-      if (lane == arg) {
-        a[j] = pa;
-        v[j] = pv;
-      } else {
-        a[j] = fma(-f, pa, a[j]);
-        v[j] = fma(-f, pv, v[j]);
-      }
+      const double sj = (j == c) ? piv : __shfl_sync(full, a[j], arg) * piv;
+      if (isp) a[j] = sj;
+      else a[j] = (j == c) ? (-f * sj) : fma(-f, sj, a[j]);
     }
   }
-  // row c of the inverse is the row held by the lane that pivoted column c
+  // stored S[r][c'] holds inverse entry (mycol(r), rc[c'])
   if (mycol >= 0) {
 #pragma unroll
-    for (int j = 0; j < m; ++j) Inv[mycol * m + j] = v[j];
+    for (int j = 0; j < m; ++j) Inv[mycol * m + rc[j]] = a[j];
   }
   __syncwarp();
 }
