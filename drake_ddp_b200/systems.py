@@ -84,7 +84,7 @@ def cart_pole_with_wall(dt=1e-2, mc=10.0, mp=1.0, length=0.5, g=9.81, ball_radiu
 
 
 def quadruped(dt=4e-3, substeps=2, mass=8.252, inertia=(0.07, 0.26, 0.242),
-              joint_inertia=(0.03, 0.03, 0.03), joint_damping=0.1,
+              joint_inertia=(0.03, 0.03, 0.03), joint_damping=1.0,
               l_abad=0.062, l_thigh=0.209, l_shank=0.19, hip_x=0.19, hip_y=0.049,
               foot_radius=0.0175, modulus=5e6, mu=0.6, v_stiction=0.2, g=9.81) -> AnalyticSystem:
     """mini_cheetah-scale lumped quadruped (masses/lengths from mini_cheetah_mesh.urdf)."""
