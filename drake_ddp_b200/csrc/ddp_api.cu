@@ -122,9 +122,9 @@ int launch_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
 }
 template <class Model>
 int launch_linearize(ddp_solver* s, const int* list, const int* count) {
-  constexpr int G = Cfg<Model>::G_LIN, K = Cfg<Model>::K_LIN;
+  constexpr int G = Cfg<Model>::G_LIN, K = Cfg<Model>::K_LIN, P = Cfg<Model>::P_LIN;
   const size_t threads = (size_t)s->d.B * s->d.T * G;
-  linearize_kernel<Model, G, K><<<cdiv(threads, 128), 128, 0, s->stream>>>(s->d, list, count);
+  linearize_kernel<Model, G, K, P><<<cdiv(threads, 128), 128, 0, s->stream>>>(s->d, list, count);
   s->launches++;
   return 0;
 }

@@ -38,7 +38,8 @@ struct Cfg {
   static constexpr bool small = (n + m) <= 8;
   static constexpr int G_ROLL = small ? 1 : 4;      // lanes per rollout candidate
   static constexpr int G_LIN = small ? 1 : 16;      // lanes per linearization point
-  static constexpr int K_LIN = (n + m + G_LIN - 1) / G_LIN;  // seed directions per lane
+  static constexpr int K_LIN = small ? (n + m) : 1; // seed directions per lane and sweep
+  static constexpr int P_LIN = (n + m + G_LIN * K_LIN - 1) / (G_LIN * K_LIN);  // sweeps
   static constexpr int BWD_THREADS = small ? 32 : 128;
 };
 
@@ -465,7 +466,7 @@ __global__ void ie_finish_kernel(Dev d) {
 // directions spread over the G lanes of a group (K per lane); lane L owns directions
 // g = k*G + L so that stores of one Jacobian row are contiguous across lanes.
 // =============================================================================================
-template <class Model, int G, int K>
+template <class Model, int G, int K, int PASSES>
 __global__ void __launch_bounds__(128) linearize_kernel(Dev d, const int* list, const int* count) {
   constexpr int n = Model::n, m = Model::m;
   typedef Dual<K> D;
@@ -478,31 +479,36 @@ __global__ void __launch_bounds__(128) linearize_kernel(Dev d, const int* list, 
   const int t = list[(size_t)b * d.T + i];
   const double* xp = d.x_bar + ((size_t)b * d.N + t) * n;
   const double* up = d.u_bar + ((size_t)b * d.T + t) * m;
-  D xs[n], us[m], out[n];
-#pragma unroll
-  for (int j = 0; j < n; ++j) {
-    xs[j].v = xp[j];
-#pragma unroll
-    for (int k = 0; k < K; ++k) xs[j].d[k] = (k * G + lane == j) ? 1.0 : 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < m; ++j) {
-    us[j].v = up[j];
-#pragma unroll
-    for (int k = 0; k < K; ++k) us[j].d[k] = (k * G + lane == n + j) ? 1.0 : 0.0;
-  }
-  Model::template step<D>(xs, us, out, d.params);
   double* fx = d.fx + ((size_t)b * d.T + t) * n * n;
   double* fu = d.fu + ((size_t)b * d.T + t) * n * m;
+  // the n+m seed directions are covered in PASSES sweeps of G*K directions each: fewer
+  // directions per lane keep the dual state in registers at the price of recomputing values
+#pragma unroll 1
+  for (int pass = 0; pass < PASSES; ++pass) {
+    D xs[n], us[m], out[n];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int g = k * G + lane;
-    if (g < n) {
+    for (int j = 0; j < n; ++j) {
+      xs[j].v = xp[j];
 #pragma unroll
-      for (int r = 0; r < n; ++r) fx[r * n + g] = out[r].d[k];
-    } else if (g < n + m) {
+      for (int k = 0; k < K; ++k) xs[j].d[k] = ((pass * K + k) * G + lane == j) ? 1.0 : 0.0;
+    }
 #pragma unroll
-      for (int r = 0; r < n; ++r) fu[r * m + (g - n)] = out[r].d[k];
+    for (int j = 0; j < m; ++j) {
+      us[j].v = up[j];
+#pragma unroll
+      for (int k = 0; k < K; ++k) us[j].d[k] = ((pass * K + k) * G + lane == n + j) ? 1.0 : 0.0;
+    }
+    Model::template step<D>(xs, us, out, d.params);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int g = (pass * K + k) * G + lane;
+      if (g < n) {
+#pragma unroll
+        for (int r = 0; r < n; ++r) fx[r * n + g] = out[r].d[k];
+      } else if (g < n + m) {
+#pragma unroll
+        for (int r = 0; r < n; ++r) fu[r * m + (g - n)] = out[r].d[k];
+      }
     }
   }
 }

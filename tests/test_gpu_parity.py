@@ -273,21 +273,27 @@ def test_full_size_c4_properties():
     s = make_gpu(prob, B=B, A=2, x0=x0)
     s.begin_solve()
     prev = np.full(B, np.inf)
+    prev_iters = np.zeros(B, dtype=np.int32)
     spot = [0, 1, 517]
     oracles = [make_oracle(prob, x0=x0[b]) for b in spot]
     Ls = [np.inf] * len(spot)
     for it in range(3):
         s.iterate()
-        cost, status = s.cost, s.status
+        cost, status, iters = s.cost, s.status, s.get_int(_lib.I_ITERS)
         ok = status != _lib.TRAJ_LINESEARCH_FAILED
+        ran = iters > prev_iters                                  # still iterating this round
         assert ok.mean() > 0.99
-        assert np.all(cost[ok] < prev[ok])                       # accepted steps decrease the cost
+        assert np.all(cost[ok & ran] < prev[ok & ran])            # accepted steps decrease the cost
+        np.testing.assert_array_equal(cost[~ran], prev[~ran])     # converged ones are frozen
+        prev_iters = iters
         np.testing.assert_array_equal(cost[-4:], cost[:4])       # duplicate seeds: bit-identical
         K = s.get(_lib.K)
         np.testing.assert_array_equal(K[-4:], K[:4])
         fx, fu, xb, ub = s.get(_lib.FX), s.get(_lib.FU), s.get(_lib.X_BAR), s.get(_lib.U_BAR)
         kappa, dV = s.get(_lib.KAPPA), s.get(_lib.DV)
         for k, b in enumerate(spot):
+            if not ran[b]:
+                continue
             rec = oracles[k].iterate(Ls[k])
             Ls[k] = rec.L
             assert abs(cost[b] - rec.L) <= 1e-7 * abs(rec.L)      # north star: 1e-5
