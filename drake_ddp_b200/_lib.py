@@ -27,7 +27,7 @@ SYMBOLS = [
     "ddp_set_initial_state", "ddp_set_initial_guess", "ddp_reset", "ddp_begin_solve",
     "ddp_iterate", "ddp_solve", "ddp_iterate_async", "ddp_sync", "ddp_run_phase", "ddp_get",
     "ddp_put", "ddp_get_int", "ddp_device_ptr", "ddp_array_elems", "ddp_last_timings",
-    "ddp_launch_count", "ddp_peak_fp64",
+    "ddp_launch_count", "ddp_peak_fp64", "ddp_mpc_shift",
 ]
 
 # enums of include/ddp_b200.h
@@ -88,6 +88,7 @@ def lib():
     L.ddp_set_initial_guess.argtypes = [c_vp, c_vp]
     L.ddp_reset.argtypes = [c_vp]
     L.ddp_begin_solve.argtypes = [c_vp]
+    L.ddp_mpc_shift.argtypes = [c_vp, c_int]
     L.ddp_iterate.argtypes = [c_vp, ip]
     L.ddp_solve.argtypes = [c_vp, c_int, ip]
     L.ddp_iterate_async.argtypes = [c_vp]

@@ -510,6 +510,17 @@ int ddp_reset(ddp_solver_t* s) {
   return ddp_begin_solve(s);
 }
 
+int ddp_mpc_shift(ddp_solver_t* s, int replan_steps) {
+  if (replan_steps < 1 || replan_steps >= s->d.N) {
+    g_err = "replan_steps must be in [1, N)";
+    return DDP_ERR_ARG;
+  }
+  mpc_shift_kernel<<<s->d.B, 64, 0, s->stream>>>(s->d, replan_steps);
+  s->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int ddp_begin_solve(ddp_solver_t* s) {
   const int B = s->d.B;
   std::vector<double> inf(B, INFINITY);

@@ -271,6 +271,21 @@ __global__ void commit_done_kernel(Dev d) {
   if (b < d.B) d.acc[b] = -1;
 }
 
+// Receding-horizon warm start on the device (acrobot.py:145-153, mini_cheetah.py:190-198):
+// u_bar <- [u_bar[:, r:], last column repeated r times];  x0 <- x_bar[:, r].
+__global__ void mpc_shift_kernel(Dev d, int r) {
+  const int b = blockIdx.x;
+  const int m = d.m, T = d.T, n = d.n;
+  double* u = d.u_bar + (size_t)b * T * m;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const double last = u[(size_t)(T - 1) * m + j];
+    for (int t = 0; t < T; ++t) u[(size_t)t * m + j] = (t + r < T) ? u[(size_t)(t + r) * m + j] : last;
+  }
+  double* x0 = const_cast<double*>(d.x0) + (size_t)b * n;
+  const double* xr = d.x_bar + ((size_t)b * d.N + r) * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) x0[j] = xr[j];
+}
+
 // reset per-iteration line-search state
 __global__ void begin_iter_kernel(Dev d, int force_all) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

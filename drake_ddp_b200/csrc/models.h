@@ -363,10 +363,11 @@ struct Quadruped {
 // joint dynamics are rotor-inertia dominated with gravity compensated; a compliant
 // sphere at the tool tip pushes a free ball (sphere/sphere contact) that rests on a
 // compliant table (sphere/plane contact) with regularised friction at both contacts.
+// Normal forces carry Hunt-Crossley dissipation: Fn = Fe(depth) * max(0, 1 + d * depth_rate).
 // p = [dt, substeps, Ij, joint_damping, d0..d6 (7), tip_radius, ball_radius, ball_mass,
-//      E, mu, v_stiction, g, base_z]
+//      E, mu, v_stiction, g, base_z, dissipation]
 struct ArmBall {
-  static constexpr int n = 27, m = 7, np = 19;
+  static constexpr int n = 27, m = 7, np = 20;
   static constexpr int COOP = 1;
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
@@ -375,7 +376,7 @@ struct ArmBall {
     const double Ij = p[2], bj = p[3];
     const double* d = p + 4;
     const double rt = p[11], rb = p[12], mb = p[13], E = p[14], mu = p[15], vs = p[16];
-    const double g = p[17], bz = p[18];
+    const double g = p[17], bz = p[18], diss = p[19];
     const double Ib = 0.4 * mb * rb * rb;
     S q[14], v[13];
 #pragma unroll
@@ -443,13 +444,16 @@ struct ArmBall {
         if (val(depth) > 0.0) {
           nx = nx / dist; ny = ny / dist; nz = nz / dist;  // tip -> ball
           const double Re = rt * rb / (rt + rb);
-          S Fn = sphere_plane_force(depth, Re, E);
           // relative velocity of ball surface point w.r.t. tip at the contact
           S cxr = -(rb)*nx, cyr = -(rb)*ny, czr = -(rb)*nz;  // contact point rel. ball centre
           S rvx = bv[0] + (w[1] * czr - w[2] * cyr) - tvx;
           S rvy = bv[1] + (w[2] * cxr - w[0] * czr) - tvy;
           S rvz = bv[2] + (w[0] * cyr - w[1] * cxr) - tvz;
-          S vn = rvx * nx + rvy * ny + rvz * nz;
+          S vn = rvx * nx + rvy * ny + rvz * nz;   // separation rate = -depth rate
+          S Fn = sphere_plane_force(depth, Re, E);
+          S hc = 1.0 - diss * vn;
+          if (val(hc) < 0.0) hc = S(0.0);
+          Fn = Fn * hc;
           S tx = rvx - vn * nx, ty = rvy - vn * ny, tz = rvz - vn * nz;
           S sl = sqrt_(tx * tx + ty * ty + tz * tz + vs * vs);
           S cfx = Fn * nx - (mu * Fn) * tx / sl;
@@ -467,6 +471,9 @@ struct ArmBall {
         S depth = rb - bz_;
         if (val(depth) > 0.0) {
           S Fn = sphere_plane_force(depth, rb, E);
+          S hc = 1.0 - diss * bv[2];
+          if (val(hc) < 0.0) hc = S(0.0);
+          Fn = Fn * hc;
           // contact point velocity: v + w x (0,0,-rb)
           S cvx = bv[0] - w[1] * rb;
           S cvy = bv[1] + w[0] * rb;

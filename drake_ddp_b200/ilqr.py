@@ -143,6 +143,11 @@ class BatchedILQR:
     def reset(self):
         _lib.check(self._L.ddp_reset(self._h), "ddp_reset")
 
+    def mpc_shift(self, replan_steps: int):
+        """Device-side receding-horizon warm start: shift the control tape by ``replan_steps``,
+        pad with the last control, x0 <- x_bar[:, replan_steps] (acrobot.py:145-153)."""
+        _lib.check(self._L.ddp_mpc_shift(self._h, int(replan_steps)), "ddp_mpc_shift")
+
     # ---- solve ----------------------------------------------------------------------------
     def begin_solve(self):
         _lib.check(self._L.ddp_begin_solve(self._h), "ddp_begin_solve")

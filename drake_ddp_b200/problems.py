@@ -135,31 +135,73 @@ def quadruped(N: int = 200, target_vel: float = 1.0, keypoints=None) -> Problem:
 
 
 # ---- arm + ball (kinova_gen3 / panda_fr3-scale) --------------------------------------
-def arm_ball(N: int = 400, keypoints="setInterval5") -> Problem:
+def arm_tip(sysm: systems.AnalyticSystem, q_arm):
+    """Tool-tip position of the 7R chain of csrc/models.h ArmBall (z, y, z, y, z, y, z axes;
+    link i goes d_i along the rotated local z)."""
+    d, bz = sysm.params[4:11], sysm.params[18]
+    R, pos = np.eye(3), np.array([0.0, 0.0, bz])
+    for i in range(7):
+        c, s_ = np.cos(q_arm[i]), np.sin(q_arm[i])
+        Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1.0]])
+        Ry = np.array([[c, 0, s_], [0, 1.0, 0], [-s_, 0, c]])
+        R = R @ (Rz if i % 2 == 0 else Ry)
+        pos = pos + d[i] * R[:, 2]
+    return pos
+
+
+def arm_ball_start(sysm: systems.AnalyticSystem, ball_xy=(0.6, 0.0), press=2e-4):
+    """Push pose (the role of q_push, kinova_gen3.py:47): elbow-up planar configuration whose
+    tool sphere presses ``press`` metres into the ball's -x side; the ball rests on the table
+    at its static penetration depth."""
+    p = sysm.params
+    rt, rb, mb, E, g = p[11], p[12], p[13], p[14], p[17]
+    depth = np.sqrt(mb * g / (np.pi * E))
+    for _ in range(50):
+        f = np.pi * E * depth ** 2 * (1 - 2 * depth / (3 * rb)) - mb * g
+        depth -= f / (2 * np.pi * E * depth * (1 - depth / rb))
+    ball = np.array([ball_xy[0], ball_xy[1], rb - depth])
+    target = ball - np.array([rt + rb - press, 0.0, 0.0])
+    q = np.array([0.0, 0.9, 0.0, 1.2, 0.0, 0.6, 0.0])
+    for _ in range(100):   # Gauss-Newton on the three pitch joints (planar IK)
+        e = arm_tip(sysm, q) - target
+        J = np.zeros((3, 3))
+        for k, j in enumerate((1, 3, 5)):
+            dq = np.zeros(7)
+            dq[j] = 1e-6
+            J[:, k] = (arm_tip(sysm, q + dq) - arm_tip(sysm, q - dq)) / 2e-6
+        step = np.linalg.lstsq(J, e, rcond=None)[0]
+        q[[1, 3, 5]] -= step
+        if np.abs(e).max() < 1e-13:
+            break
+    return q, ball
+
+
+def arm_ball(N: int = 400, keypoints="setInterval5", scenario="forward") -> Problem:
     """kinova_gen3.py:32-99,252-275 re-expressed for the analytic 7R arm + ball model
     (script horizon 50; config C5 uses N=400 with derivative interpolation on)."""
     sysm = systems.arm_ball(dt=1e-2)
     dt = sysm.dt
-    p = sysm.params
-    rb = p[12]
-    q_arm = np.array([0.0, 0.9, 0.0, 1.2, 0.0, 0.6, 0.0])
-    ball_q = np.array([1.0, 0.0, 0.0, 0.0, 0.62, 0.0, rb - 3e-4])
+    q_arm, ball = arm_ball_start(sysm)
+    ball_q = np.hstack([[1.0, 0.0, 0.0, 0.0], ball])
     x0 = np.hstack([q_arm, ball_q, np.zeros(13)])
     x_nom = x0.copy()
-    x_nom[11] += 0.15               # push the ball 15 cm (kinova_gen3.py:75-77)
-    Qq = np.hstack([np.zeros(7), [0, 0, 0, 0, 100, 100, 100]])
+    if scenario == "forward":
+        x_nom[11] += 0.2            # move the ball forward (kinova_gen3.py:57-58)
+    else:
+        x_nom[12] += 0.15           # move it to the side (kinova_gen3.py:59-60)
+    Qq = np.hstack([np.zeros(7), [0, 0, 0, 0, 100, 100, 100]])      # kinova_gen3.py:74-76
     Qv = 0.1 * np.ones(13)
     Q = np.diag(np.hstack([Qq, Qv]))
     R = 0.01 * np.eye(7)
     Qfv = Qv.copy()
-    Qfv[7:] *= 10.0
+    Qfv[7:] *= 10.0                                                  # 10*Qv_ball, :84
     Qf = np.diag(np.hstack([Qq, Qfv]))
     if keypoints == "setInterval5":
         keypoints = derivs_interpolation("setInterval", 5, 40, 1e-4, 1e-2)
     elif keypoints == "adaptiveJerk":
-        keypoints = derivs_interpolation("adaptiveJerk", 5, 40, 1e-4, 1e-2)
+        keypoints = derivs_interpolation("adaptiveJerk", 5, 40, 1e-4, 1e-2)   # kinova_gen3.py:37-42
     return Problem("arm_ball", sysm, N, x0, x_nom, dt * Q, dt * R, Qf, np.zeros((7, N - 1)),
-                   beta=0.5, delta=1e-3, gamma=0.0, keypoints=keypoints, sigma=0.01)
+                   beta=0.5, delta=1e-3, gamma=0.0, keypoints=keypoints, sigma=0.002)
 
 
 def affine_sin(n=4, m=1, N=40, seed=0, keypoints=None) -> Problem:

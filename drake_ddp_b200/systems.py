@@ -93,12 +93,15 @@ def quadruped(dt=4e-3, substeps=2, mass=8.252, inertia=(0.07, 0.26, 0.242),
     return AnalyticSystem("quadruped", MODEL_QUADRUPED, 36, 12, np.array(p, dtype=np.float64))
 
 
-def arm_ball(dt=1e-2, substeps=2, joint_inertia=0.3, joint_damping=0.5,
+def arm_ball(dt=1e-2, substeps=4, joint_inertia=0.3, joint_damping=0.5,
              links=(0.28, 0.0, 0.42, 0.0, 0.31, 0.0, 0.17), tip_radius=0.04, ball_radius=0.1,
-             ball_mass=0.1, modulus=5e5, mu=0.5, v_stiction=0.05, g=9.81, base_z=0.0) -> AnalyticSystem:
-    """kinova_gen3 / panda_fr3-scale 7R arm pushing a free ball on a table (n=27, m=7)."""
+             ball_mass=0.5, modulus=5e5, mu=0.3, v_stiction=0.05, g=9.81, base_z=0.0,
+             dissipation=5.0) -> AnalyticSystem:
+    """kinova_gen3 / panda_fr3-scale 7R arm pushing a free ball on a table (n=27, m=7); ball
+    radius, dissipation and friction from kinova_gen3.py:51,91-96; the modulus is 10x softer
+    than the script's 5e6 so the explicit contact stays well inside its stability limit."""
     p = [dt, float(substeps), joint_inertia, joint_damping, *links, tip_radius, ball_radius,
-         ball_mass, modulus, mu, v_stiction, g, base_z]
+         ball_mass, modulus, mu, v_stiction, g, base_z, dissipation]
     return AnalyticSystem("arm_ball", MODEL_ARM_BALL, 27, 7, np.array(p, dtype=np.float64))
 
 

@@ -123,6 +123,11 @@ int ddp_set_initial_guess(ddp_solver_t* s, const double* u_guess);
 /* Back to a freshly constructed object's trajectory state (zeros), keeping costs/options. */
 int ddp_reset(ddp_solver_t* s);
 
+/* Receding-horizon warm start without a host round trip (the np.block shift of
+ * acrobot.py:145-153 / mini_cheetah.py:190-198): u_bar <- [u_bar[:, r:], last column x r],
+ * x0 <- x_bar[:, r] for every trajectory.  K, kappa, x_bar stay (stale-state semantics). */
+int ddp_mpc_shift(ddp_solver_t* s, int replan_steps);
+
 /* Solve(), ilqr.py:669-710, split so the host can print the per-iteration table:
  * ddp_begin_solve sets L = inf, improvement = inf for every trajectory (ilqr.py:681-682);
  * ddp_iterate runs one forward pass + backward pass (ilqr.py:695-697) for every

@@ -35,6 +35,9 @@ CASES = {
     "affine_4_1_iterativeError": (lambda: problems.affine_sin(4, 1, 40),
                                   derivs_interpolation("iterativeError", 2, 0, 0, 1e-9), 3),
     "affine_27_7_N30": (lambda: problems.affine_sin(27, 7, 30), None, 3),
+    "arm_ball_N40": (lambda: problems.arm_ball(40, keypoints=None), None, 3),
+    "arm_ball_N40_setInterval5": (lambda: problems.arm_ball(40),
+                                  derivs_interpolation("setInterval", 5, 40, 1e-4, 1e-2), 2),
     "quadruped_N30": (lambda: problems.quadruped(30), None, 3),
     "quadruped_N30_adaptiveJerk": (lambda: problems.quadruped(30),
                                    derivs_interpolation("adaptiveJerk", 2, 20, 0.3, 10), 3),
