@@ -157,7 +157,7 @@ backward_mma_kernel(Dev d) {
     const double* Fx = s.Fx[buf];
     const double* Fu = s.Fu[buf];
 
-    // ---------------- phase 1: Wu = Vxx fu ; last warp: Qx, Qu ----------------------------------
+    // ---------------- phase 1: Wu = Vxx fu and Qx (per strip) ; last warp: Qu -------------------
     if (warp < TN) {
       const int w = warp;
       double accu[TM][2];
@@ -176,32 +176,34 @@ backward_mma_kernel(Dev d) {
         if (r < n && c < m) s.Wu[r * m + c] = accu[nt][0];
         if (r < n && c + 1 < m) s.Wu[r * m + c + 1] = accu[nt][1];
       }
-    } else {
-      // Qx = lx + fx' Vx ; Qu = lu + fu' Vx                      (ilqr.py:651-652,180-181)
-      const double* xb = s.xb[buf];
-      const double* ub = s.ub[buf];
-      for (int k = lane; k < n; k += 32) {
-        double a = 0.0, c = 0.0;
-        if (d.diag_cost) {
-          a = 2.0 * Q[k * n + k] * xb[k];
-          c = 2.0 * xnom[k] * Q[k * n + k];
-        } else {
-          for (int j = 0; j < n; ++j) {
-            a = fma(2.0 * Q[k * n + j], xb[j], a);
-            c = fma(2.0 * xnom[j], Q[j * n + k], c);
+      // Qx[k] = lx[k] + sum_i fx[i][k] Vx[i] for the 8 columns of this strip   (ilqr.py:651,180)
+      // lane = (column g8, quarter q4 of the i range); quarters are combined with two shuffles
+      {
+        const double* xb = s.xb[buf];
+        const int g8 = lane & 7, q4 = lane >> 3, k = 8 * w + g8;
+        double q = 0.0;
+        if (k < n) {
+          for (int i = q4; i < n; i += 4) q = fma(Fx[i * n + k], s.Vx[i], q);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 8);
+        q += __shfl_xor_sync(0xffffffffu, q, 16);
+        if (q4 == 0 && k < n) {
+          double a = 0.0, c = 0.0;
+          if (d.diag_cost) {
+            a = 2.0 * Q[k * n + k] * xb[k];
+            c = 2.0 * xnom[k] * Q[k * n + k];
+          } else {
+            for (int j = 0; j < n; ++j) {
+              a = fma(2.0 * Q[k * n + j], xb[j], a);
+              c = fma(2.0 * xnom[j], Q[j * n + k], c);
+            }
           }
+          s.Qx[k] = (a - c) + q;
         }
-        double q0 = a - c, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-        int i = 0;
-        for (; i + 3 < n; i += 4) {
-          q0 = fma(Fx[i * n + k], s.Vx[i], q0);
-          q1 = fma(Fx[(i + 1) * n + k], s.Vx[i + 1], q1);
-          q2 = fma(Fx[(i + 2) * n + k], s.Vx[i + 2], q2);
-          q3 = fma(Fx[(i + 3) * n + k], s.Vx[i + 3], q3);
-        }
-        for (; i < n; ++i) q0 = fma(Fx[i * n + k], s.Vx[i], q0);
-        s.Qx[k] = (q0 + q1) + (q2 + q3);
       }
+    } else {
+      // Qu = lu + fu' Vx                                          (ilqr.py:652,181)
+      const double* ub = s.ub[buf];
       for (int r = lane; r < m; r += 32) {
         double a = 0.0;
         for (int j = 0; j < m; ++j) a = fma(2.0 * R[r * m + j], ub[j], a);
@@ -217,10 +219,25 @@ backward_mma_kernel(Dev d) {
     }
     __syncthreads();
 
-    // ---------------- phase 2: strips: W = Vxx fx, then Qxx (into Vxx) and Qux ------------------
-    // ---------------- meanwhile the last warp: Quu, its inverse, kappa, g -----------------------
+    // ---------------- phase 2 ---------------------------------------------------------------
+    // strips: Quu tiles first (hand-off to the last warp through named barrier 2), then
+    // W = Vxx fx, then Qxx (into Vxx) and Qux.  Last warp: waits for Quu, inverts it.
     if (warp < TN) {
       const int w = warp;
+      // Quu = luu + fu' Wu                                        (ilqr.py:654)
+      for (int q = w; q < TM * TM; q += TN) {
+        const int mt = q / TM, nt = q % TM;
+        double a2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kk = 0; kk < KN; ++kk) {
+          const int k = 4 * kk + tg;
+          dmma(a2, ldz(Fu, m, k, 8 * mt + g, n, m), ldz(s.Wu, m, k, 8 * nt + g, n, m));
+        }
+        const int r = 8 * mt + g, c = 8 * nt + 2 * tg;
+        if (r < m && c < m) s.Quu[r * m + c] = 2.0 * R[r * m + c] + a2[0];
+        if (r < m && c + 1 < m) s.Quu[r * m + c + 1] = 2.0 * R[r * m + c + 1] + a2[1];
+      }
+      asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");
       {
         double acc[TN][2];
 #pragma unroll
@@ -268,37 +285,12 @@ backward_mma_kernel(Dev d) {
         if (r < m && c + 1 < n) s.Qux[r * n + c + 1] = au[mt][1];
       }
     } else {
-      // Quu = luu + fu' Wu                                        (ilqr.py:654)
-#pragma unroll
-      for (int mt = 0; mt < TM; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < TM; ++nt) {
-          double a2[2] = {0.0, 0.0};
-#pragma unroll
-          for (int kk = 0; kk < KN; ++kk) {
-            const int k = 4 * kk + tg;
-            dmma(a2, ldz(Fu, m, k, 8 * mt + g, n, m), ldz(s.Wu, m, k, 8 * nt + g, n, m));
-          }
-          const int r = 8 * mt + g, c = 8 * nt + 2 * tg;
-          if (r < m && c < m) s.Quu[r * m + c] = 2.0 * R[r * m + c] + a2[0];
-          if (r < m && c + 1 < m) s.Quu[r * m + c + 1] = 2.0 * R[r * m + c + 1] + a2[1];
-        }
-      __syncwarp();
+      asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");
       invert_warp<m>(s.Quu, s.Inv);                               // ilqr.py:655
-      // kappa = Quu^-1 Qu ; g = Qu' Quu^-1                         (ilqr.py:659,663)
-      for (int r = lane; r < m; r += 32) {
-        double a = 0.0, c = 0.0;
-        for (int j = 0; j < m; ++j) {
-          a = fma(s.Inv[r * m + j], s.Qu[j], a);
-          c = fma(s.Qu[j], s.Inv[j * m + r], c);
-        }
-        s.kap[r] = a;
-        s.g[r] = c;
-      }
     }
     __syncthreads();
 
-    // ---------------- phase 3: K = Quu^-1 Qux ; Vxx = Qxx - Qux' K ; Vx, dV, outputs ---------
+    // ---------------- phase 3: K = Quu^-1 Qux ; Vxx = Qxx - Qux' K ; last warp: kappa, dV, Vx ---
     if (warp < TN) {
       const int w = warp;
       double ak[TM][2];
@@ -342,13 +334,23 @@ backward_mma_kernel(Dev d) {
         if (r < n && c + 1 < n) s.Vxx[r * n + c + 1] -= av[mt][1];
       }
     } else {
-      for (int r = lane; r < m; r += 32) d.kappa[((size_t)b * T + t) * m + r] = s.kap[r];
+      // kappa = Quu^-1 Qu ; g = Qu' Quu^-1 ; dV = g Qu ; Vx = Qx - g Qux   (ilqr.py:659,663,666)
+      for (int r = lane; r < m; r += 32) {
+        double a = 0.0, c = 0.0;
+        for (int j = 0; j < m; ++j) {
+          a = fma(s.Inv[r * m + j], s.Qu[j], a);
+          c = fma(s.Qu[j], s.Inv[j * m + r], c);
+        }
+        s.g[r] = c;
+        d.kappa[((size_t)b * T + t) * m + r] = a;
+      }
+      __syncwarp();
       if (lane == 0) {
         double a = 0.0;
         for (int j = 0; j < m; ++j) a = fma(s.g[j], s.Qu[j], a);
-        d.dV[(size_t)b * T + t] = a;                              // ilqr.py:663
+        d.dV[(size_t)b * T + t] = a;
       }
-      for (int k = lane; k < n; k += 32) {                        // Vx = Qx - Qu' Quu^-1 Qux (:666)
+      for (int k = lane; k < n; k += 32) {
         double a = 0.0;
         for (int j = 0; j < m; ++j) a = fma(s.g[j], s.Qux[j * n + k], a);
         s.Vx[k] = s.Qx[k] - a;

@@ -107,6 +107,18 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int pe
     const double* xb = d.x_bar + ((size_t)b * N + t) * n;
     const double* ub = d.u_bar + ((size_t)b * T + t) * m;
     const double* kp = d.kappa + ((size_t)b * T + t) * m;
+    // pull the next step's gain rows towards L2/L1 while this step computes
+    if (t + 1 < T) {
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + G * i;
+        if (r < m) {
+          const char* pr = reinterpret_cast<const char*>(Kt + (size_t)m * n + (size_t)r * n);
+#pragma unroll
+          for (int off = 0; off < n * 8; off += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + off));
+        }
+      }
+    }
     // u_t = u_bar_t - eps*kappa_t - K_t (x_t - x_bar_t)            (ilqr.py:313)
     double dx[n];
 #pragma unroll
