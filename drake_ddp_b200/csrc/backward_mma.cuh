@@ -63,27 +63,28 @@ struct BwdMmaCfg {
   // bulk TMA needs 16-byte sizes and 16-byte aligned tile starts in global memory
   static constexpr bool TMA = ((n * n) % 2 == 0) && ((n * m) % 2 == 0) && (n % 2 == 0) && (m % 2 == 0);
   static constexpr int even(int v) { return (v + 1) & ~1; }
+  static constexpr int MINB = (n <= 36) ? 4 : 3;  // CTAs per SM the register budget is sized for
 };
 
 template <int n, int m>
 struct BwdMmaSmem {
   typedef BwdMmaCfg<n, m> C;
-  alignas(16) double Fx[2][C::even(n * n)];
-  alignas(16) double Fu[2][C::even(n * m)];
+  alignas(16) double Fx[2][C::even(n * n)];   // double-buffered bulk-TMA destination
+  alignas(16) double Fu[C::even(n * m)];      // single buffer: refilled after phase 2 (dead by then)
   alignas(16) double xb[2][C::even(n)];
   alignas(16) double ub[2][C::even(m)];
   alignas(16) double Vxx[n * n];
   double W[n * n];
-  double Wu[n * m];
+  double WuKt[n * m];   // Wu = Vxx fu (phases 1-2), then K_t (phase 3)
   double Qux[m * n];
-  double Kt[m * n];
-  double Quu[m * m], Inv[m * m];
-  double Vx[n], Qx[n], Qu[m], g[m], kap[m];
+  double QuuInv[m * m]; // Quu, overwritten by its inverse
+  double Vx[n], Qx[n], Qu[m], g[m];
   alignas(8) uint64_t bar[2];
+  alignas(8) uint64_t barFu;
 };
 
 template <class Model>
-__global__ void __launch_bounds__(BwdMmaCfg<Model::n, Model::m>::NT, 3)
+__global__ void __launch_bounds__(BwdMmaCfg<Model::n, Model::m>::NT, BwdMmaCfg<Model::n, Model::m>::MINB)
 backward_mma_kernel(Dev d) {
   constexpr int n = Model::n, m = Model::m;
   typedef BwdMmaCfg<n, m> C;
@@ -102,18 +103,21 @@ backward_mma_kernel(Dev d) {
   const double* gfu = d.fu + (size_t)b * T * n * m;
   const double* gxb = d.x_bar + (size_t)b * N * n;
   const double* gub = d.u_bar + (size_t)b * T * m;
-  constexpr uint32_t kStageBytes = (n * n + n * m + n + m) * 8;
+  constexpr uint32_t kStageBytes = (n * n + n + m) * 8;
 
   auto issue_tile = [&](int t, int buf) {   // one thread
     mbar_expect_tx(&s.bar[buf], kStageBytes);
     tma_load_1d(s.Fx[buf], gfx + (size_t)t * n * n, n * n * 8, &s.bar[buf]);
-    tma_load_1d(s.Fu[buf], gfu + (size_t)t * n * m, n * m * 8, &s.bar[buf]);
     tma_load_1d(s.xb[buf], gxb + (size_t)t * n, n * 8, &s.bar[buf]);
     tma_load_1d(s.ub[buf], gub + (size_t)t * m, m * 8, &s.bar[buf]);
   };
+  auto issue_fu = [&](int t) {              // one thread
+    mbar_expect_tx(&s.barFu, n * m * 8);
+    tma_load_1d(s.Fu, gfu + (size_t)t * n * m, n * m * 8, &s.barFu);
+  };
   auto copy_tile = [&](int t, int buf) {    // all threads (fallback)
     for (int i = tid; i < n * n; i += NT) s.Fx[buf][i] = gfx[(size_t)t * n * n + i];
-    for (int i = tid; i < n * m; i += NT) s.Fu[buf][i] = gfu[(size_t)t * n * m + i];
+    for (int i = tid; i < n * m; i += NT) s.Fu[i] = gfu[(size_t)t * n * m + i];
     for (int i = tid; i < n; i += NT) s.xb[buf][i] = gxb[(size_t)t * n + i];
     for (int i = tid; i < m; i += NT) s.ub[buf][i] = gub[(size_t)t * m + i];
   };
@@ -122,10 +126,14 @@ backward_mma_kernel(Dev d) {
     if (tid == 0) {
       mbar_init(&s.bar[0], 1);
       mbar_init(&s.bar[1], 1);
+      mbar_init(&s.barFu, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) issue_tile(T - 1, 0);
+    if (tid == 0) {
+      issue_tile(T - 1, 0);
+      issue_fu(T - 1);
+    }
   }
 
   // Vx, Vxx <- terminal cost partials at x_bar[:, -1]            (ilqr.py:638, 203-204)
@@ -144,18 +152,21 @@ backward_mma_kernel(Dev d) {
   __syncthreads();
 
   uint32_t parity[2] = {0, 0};
+  uint32_t parityFu = 0;
   int buf = 0;
   for (int t = T - 1; t >= 0; --t, buf ^= 1) {
     if (C::TMA) {
       if (tid == 0 && t > 0) issue_tile(t - 1, buf ^ 1);
       mbar_wait(&s.bar[buf], parity[buf]);
       parity[buf] ^= 1;
+      mbar_wait(&s.barFu, parityFu);
+      parityFu ^= 1;
     } else {
       copy_tile(t, buf);
       __syncthreads();
     }
     const double* Fx = s.Fx[buf];
-    const double* Fu = s.Fu[buf];
+    const double* Fu = s.Fu;
 
     // ---------------- phase 1: Wu = Vxx fu and Qx (per strip) ; last warp: Qu -------------------
     if (warp < TN) {
@@ -173,8 +184,8 @@ backward_mma_kernel(Dev d) {
 #pragma unroll
       for (int nt = 0; nt < TM; ++nt) {
         const int r = 8 * w + g, c = 8 * nt + 2 * tg;
-        if (r < n && c < m) s.Wu[r * m + c] = accu[nt][0];
-        if (r < n && c + 1 < m) s.Wu[r * m + c + 1] = accu[nt][1];
+        if (r < n && c < m) s.WuKt[r * m + c] = accu[nt][0];
+        if (r < n && c + 1 < m) s.WuKt[r * m + c + 1] = accu[nt][1];
       }
       // Qx[k] = lx[k] + sum_i fx[i][k] Vx[i] for the 8 columns of this strip   (ilqr.py:651,180)
       // lane = (column g8, quarter q4 of the i range); quarters are combined with two shuffles
@@ -231,11 +242,11 @@ backward_mma_kernel(Dev d) {
 #pragma unroll
         for (int kk = 0; kk < KN; ++kk) {
           const int k = 4 * kk + tg;
-          dmma(a2, ldz(Fu, m, k, 8 * mt + g, n, m), ldz(s.Wu, m, k, 8 * nt + g, n, m));
+          dmma(a2, ldz(Fu, m, k, 8 * mt + g, n, m), ldz(s.WuKt, m, k, 8 * nt + g, n, m));
         }
         const int r = 8 * mt + g, c = 8 * nt + 2 * tg;
-        if (r < m && c < m) s.Quu[r * m + c] = 2.0 * R[r * m + c] + a2[0];
-        if (r < m && c + 1 < m) s.Quu[r * m + c + 1] = 2.0 * R[r * m + c + 1] + a2[1];
+        if (r < m && c < m) s.QuuInv[r * m + c] = 2.0 * R[r * m + c] + a2[0];
+        if (r < m && c + 1 < m) s.QuuInv[r * m + c + 1] = 2.0 * R[r * m + c + 1] + a2[1];
       }
       asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");
       {
@@ -286,9 +297,12 @@ backward_mma_kernel(Dev d) {
       }
     } else {
       asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");
-      invert_warp<m>(s.Quu, s.Inv);                               // ilqr.py:655
+      invert_warp<m>(s.QuuInv, s.QuuInv);                               // ilqr.py:655
     }
     __syncthreads();
+
+    // fu of this step is dead now: refill the single Fu buffer with the next step's tile
+    if (C::TMA && tid == 0 && t > 0) issue_fu(t - 1);
 
     // ---------------- phase 3: K = Quu^-1 Qux ; Vxx = Qxx - Qux' K ; last warp: kappa, dV, Vx ---
     if (warp < TN) {
@@ -301,18 +315,18 @@ backward_mma_kernel(Dev d) {
         const int k = 4 * kk + tg;
         const double bf = ldz(s.Qux, n, k, 8 * w + g, m, n);
 #pragma unroll
-        for (int mt = 0; mt < TM; ++mt) dmma(ak[mt], ldz(s.Inv, m, 8 * mt + g, k, m, m), bf);
+        for (int mt = 0; mt < TM; ++mt) dmma(ak[mt], ldz(s.QuuInv, m, 8 * mt + g, k, m, m), bf);
       }
       double* gK = d.K + ((size_t)b * T + t) * m * n;
 #pragma unroll
       for (int mt = 0; mt < TM; ++mt) {
         const int r = 8 * mt + g, c = 8 * w + 2 * tg;
         if (r < m && c < n) {
-          s.Kt[r * n + c] = ak[mt][0];
+          s.WuKt[r * n + c] = ak[mt][0];
           gK[r * n + c] = ak[mt][0];
         }
         if (r < m && c + 1 < n) {
-          s.Kt[r * n + c + 1] = ak[mt][1];
+          s.WuKt[r * n + c + 1] = ak[mt][1];
           gK[r * n + c + 1] = ak[mt][1];
         }
       }
@@ -323,7 +337,7 @@ backward_mma_kernel(Dev d) {
 #pragma unroll
       for (int kk = 0; kk < KM; ++kk) {
         const int k = 4 * kk + tg;
-        const double bf = ldz(s.Kt, n, k, 8 * w + g, m, n);
+        const double bf = ldz(s.WuKt, n, k, 8 * w + g, m, n);
 #pragma unroll
         for (int mt = 0; mt < TN; ++mt) dmma(av[mt], ldz(s.Qux, n, k, 8 * mt + g, m, n), bf);
       }
@@ -338,8 +352,8 @@ backward_mma_kernel(Dev d) {
       for (int r = lane; r < m; r += 32) {
         double a = 0.0, c = 0.0;
         for (int j = 0; j < m; ++j) {
-          a = fma(s.Inv[r * m + j], s.Qu[j], a);
-          c = fma(s.Qu[j], s.Inv[j * m + r], c);
+          a = fma(s.QuuInv[r * m + j], s.Qu[j], a);
+          c = fma(s.Qu[j], s.QuuInv[j * m + r], c);
         }
         s.g[r] = c;
         d.kappa[((size_t)b * T + t) * m + r] = a;

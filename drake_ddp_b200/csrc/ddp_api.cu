@@ -12,6 +12,7 @@
 #include "../../include/ddp_b200.h"
 #include "kernels.cuh"
 #include "backward_mma.cuh"
+#include "quadruped_linearize.cuh"
 
 using namespace ddp;
 
@@ -37,6 +38,11 @@ struct ddp_solver {
   long long launches;
   bool timings_valid;
   bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
+  bool quad_structured;  // opt-in (DDP_QUAD_STRUCTURED=1): structured quadruped linearization
+  double* quadG;         // quadruped fast path: local leg Jacobians [B*T][sub][4][144]
+  double* quadXmid;      //                      state after each substep [B*T][sub][36]
+  int quad_sub;          // substeps of the quadruped model (0: fast path unavailable)
+  unsigned long long* quadTab;  // gather descriptors of the substep Jacobian assembly
   // array table
   double* darr[16];
   size_t dsize[16];
@@ -58,7 +64,8 @@ struct Carver {
 
 constexpr int kMaxEps = 2048;
 
-void carve(Dev& d, double** params, int np, Carver& c) {
+void carve(Dev& d, double** params, int np, Carver& c, int model, double** quadG, double** quadXmid,
+           unsigned long long** quadTab) {
   const size_t B = d.B, N = d.N, T = d.T, n = d.n, m = d.m, A = d.A;
   *params = c.take<double>(np);
   d.Q = c.take<double>(n * n);
@@ -102,6 +109,14 @@ void carve(Dev& d, double** params, int np, Carver& c) {
   d.nseg[1] = c.take<int>(B);
   d.evallist = c.take<int>(B * T);
   d.evalcount = c.take<int>(B);
+  *quadG = nullptr;
+  *quadXmid = nullptr;
+  *quadTab = nullptr;
+  if (model == MODEL_QUADRUPED) {
+    *quadG = c.take<double>(((B * T + 7) / 8) * 2 * 144 * 32);
+    *quadXmid = c.take<double>(B * T * 2 * 36);
+    *quadTab = c.take<unsigned long long>(kQuadTabSize);
+  }
 }
 
 int model_dims(int model_id, int* n, int* m, int* np) {
@@ -172,7 +187,19 @@ int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
   DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base, per_traj, n_items));
   return 0;
 }
+int launch_quad_linearize(ddp_solver* s, const int* list, const int* count) {
+  const size_t items = (size_t)s->d.B * s->d.T;
+  quad_legjac_kernel<<<cdiv(items * 4, 128), 128, 0, s->stream>>>(s->d, list, count, s->quadG, s->quadXmid,
+                                                                    s->quad_sub);
+  s->launches++;
+  quad_chain_kernel<<<(unsigned)items, kQuadThreads, 0, s->stream>>>(s->d, list, count, s->quadG, s->quadXmid,
+                                                                      s->quadTab, s->quad_sub);
+  s->launches++;
+  return 0;
+}
 int do_linearize(ddp_solver* s, const int* list, const int* count) {
+  if (s->model == MODEL_QUADRUPED && s->quad_sub > 0 && s->quad_structured)
+    return launch_quad_linearize(s, list, count);
   DDP_MODEL_SWITCH(s->model, return launch_linearize<Model>(s, list, count));
   return 0;
 }
@@ -348,8 +375,9 @@ size_t ddp_workspace_bytes(int model_id, int N, int B, int A) {
   d.B = B;
   d.A = A;
   Carver c{nullptr, 0};
-  double* p;
-  carve(d, &p, np, c);
+  double *p, *g1, *g2;
+  unsigned long long* g3;
+  carve(d, &p, np, c, model_id, &g1, &g2, &g3);
   return c.off + 256;
 }
 
@@ -380,10 +408,21 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   d.n = n; d.m = m; d.N = N; d.T = N - 1; d.B = B; d.A = A;
   Carver c{(char*)workspace_dev, 0};
   double* params;
-  carve(d, &params, np, c);
+  carve(d, &params, np, c, model_id, &s->quadG, &s->quadXmid, &s->quadTab);
+  s->quad_sub = 0;
+  if (model_id == MODEL_QUADRUPED) {
+    const int sub = (int)params_host[1];
+    if (sub == 1 || sub == 2) s->quad_sub = sub;
+  }
+  s->quad_structured = getenv("DDP_QUAD_STRUCTURED") != nullptr;
   d.params = params;
   CK(cudaMemsetAsync(workspace_dev, 0, c.off, s->stream));
   CK(cudaMemcpyAsync(params, params_host, np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (s->quadTab) {
+    static unsigned long long tab[kQuadTabSize];
+    quad_build_table(tab);
+    CK(cudaMemcpyAsync(s->quadTab, tab, sizeof(tab), cudaMemcpyHostToDevice, s->stream));
+  }
   CK(cudaHostAlloc(&s->h_counters, 4 * sizeof(int), cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&s->ev[i]));
   // Q = R = Qf = I (ilqr.py:65-67)

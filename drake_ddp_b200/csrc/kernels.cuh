@@ -37,8 +37,14 @@ struct Cfg {
   static constexpr int n = Model::n, m = Model::m;
   static constexpr bool small = (n + m) <= 8;
   static constexpr int G_ROLL = small ? 1 : 4;      // lanes per rollout candidate
-  static constexpr int G_LIN = small ? 1 : 16;      // lanes per linearization point
-  static constexpr int K_LIN = small ? (n + m) : 1; // seed directions per lane and sweep
+#ifndef DDP_LIN_G
+#define DDP_LIN_G 16
+#endif
+#ifndef DDP_LIN_K
+#define DDP_LIN_K 1
+#endif
+  static constexpr int G_LIN = small ? 1 : DDP_LIN_G;      // lanes per linearization point
+  static constexpr int K_LIN = small ? (n + m) : DDP_LIN_K; // seed directions per lane and sweep
   static constexpr int P_LIN = (n + m + G_LIN * K_LIN - 1) / (G_LIN * K_LIN);  // sweeps
   static constexpr int BWD_THREADS = small ? 32 : 128;
 };
@@ -493,8 +499,11 @@ __global__ void ie_finish_kernel(Dev d) {
 // directions spread over the G lanes of a group (K per lane); lane L owns directions
 // g = k*G + L so that stores of one Jacobian row are contiguous across lanes.
 // =============================================================================================
+#ifndef DDP_LIN_MINB
+#define DDP_LIN_MINB 2
+#endif
 template <class Model, int G, int K, int PASSES>
-__global__ void __launch_bounds__(128) linearize_kernel(Dev d, const int* list, const int* count) {
+__global__ void __launch_bounds__(128, (Model::n > 8 ? DDP_LIN_MINB : 1)) linearize_kernel(Dev d, const int* list, const int* count) {
   constexpr int n = Model::n, m = Model::m;
   typedef Dual<K> D;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,7 +622,9 @@ __device__ void invert_warp(const double* A, double* Inv) {
       else a[j] = (j == c) ? (-f * sj) : fma(-f, sj, a[j]);
     }
   }
-  // stored S[r][c'] holds inverse entry (mycol(r), rc[c'])
+  // stored S[r][c'] holds inverse entry (mycol(r), rc[c']); A may alias Inv: every lane loaded
+  // its row before the first shuffle, so all reads precede these writes
+  __syncwarp();
   if (mycol >= 0) {
 #pragma unroll
     for (int j = 0; j < m; ++j) Inv[mycol * m + rc[j]] = a[j];

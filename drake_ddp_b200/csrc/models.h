@@ -263,6 +263,30 @@ struct Quadruped {
     acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) / Iz;
   }
 
+  // one semi-implicit Euler substep of length h, in place
+  template <class S>
+  DDP_HD static void substep(S* q, S* v, const S* u, const double* p, double h) {
+    BasePose<S> B;
+    base_pose(q, B);
+    LegOut<S> o[4];
+    S acc[18];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      leg((l < 2) ? 1.0 : -1.0, (l & 1) ? 1.0 : -1.0, q[6 + 3 * l], q[7 + 3 * l], q[8 + 3 * l],
+          v[6 + 3 * l], v[7 + 3 * l], v[8 + 3 * l], u[3 * l], u[3 * l + 1], u[3 * l + 2], q[2], v, B, p,
+          o[l]);
+      acc[6 + 3 * l] = o[l].a0;
+      acc[7 + 3 * l] = o[l].a1;
+      acc[8 + 3 * l] = o[l].a2;
+    }
+    // pairwise sums (same association as the 4-lane butterfly in step_coop)
+    base_acc((o[0].Fx + o[1].Fx) + (o[2].Fx + o[3].Fx), (o[0].Fy + o[1].Fy) + (o[2].Fy + o[3].Fy),
+             (o[0].Fz + o[1].Fz) + (o[2].Fz + o[3].Fz), (o[0].Tx + o[1].Tx) + (o[2].Tx + o[3].Tx),
+             (o[0].Ty + o[1].Ty) + (o[2].Ty + o[3].Ty), (o[0].Tz + o[1].Tz) + (o[2].Tz + o[3].Tz), v, p,
+             acc);
+    integrate(q, v, acc, B, h);
+  }
+
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const int sub = (int)p[1];
@@ -273,27 +297,7 @@ struct Quadruped {
       q[i] = x[i];
       v[i] = x[18 + i];
     }
-    for (int it = 0; it < sub; ++it) {
-      BasePose<S> B;
-      base_pose(q, B);
-      LegOut<S> o[4];
-      S acc[18];
-#pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        leg((l < 2) ? 1.0 : -1.0, (l & 1) ? 1.0 : -1.0, q[6 + 3 * l], q[7 + 3 * l], q[8 + 3 * l],
-            v[6 + 3 * l], v[7 + 3 * l], v[8 + 3 * l], u[3 * l], u[3 * l + 1], u[3 * l + 2], q[2], v, B, p,
-            o[l]);
-        acc[6 + 3 * l] = o[l].a0;
-        acc[7 + 3 * l] = o[l].a1;
-        acc[8 + 3 * l] = o[l].a2;
-      }
-      // pairwise sums (same association as the 4-lane butterfly in step_coop)
-      base_acc((o[0].Fx + o[1].Fx) + (o[2].Fx + o[3].Fx), (o[0].Fy + o[1].Fy) + (o[2].Fy + o[3].Fy),
-               (o[0].Fz + o[1].Fz) + (o[2].Fz + o[3].Fz), (o[0].Tx + o[1].Tx) + (o[2].Tx + o[3].Tx),
-               (o[0].Ty + o[1].Ty) + (o[2].Ty + o[3].Ty), (o[0].Tz + o[1].Tz) + (o[2].Tz + o[3].Tz), v, p,
-               acc);
-      integrate(q, v, acc, B, h);
-    }
+    for (int it = 0; it < sub; ++it) substep(q, v, u, p, h);
 #pragma unroll
     for (int i = 0; i < 18; ++i) {
       xn[i] = q[i];

@@ -311,3 +311,32 @@ def test_full_size_c4_properties():
                 assert np.abs(fx[b, t] - fxo).max() < 1e-9 * max(1.0, np.abs(fxo).max())
                 assert np.abs(fu[b, t] - fuo).max() < 1e-9 * max(1.0, np.abs(fuo).max())
         prev = cost
+
+
+def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
+    """The opt-in structured quadruped linearization (closed-form leg Jacobians + DMMA chain,
+    csrc/quadruped_linearize.cuh, DDP_QUAD_STRUCTURED=1) against the default forward-mode-AD
+    kernel on the same points, in contact and in flight."""
+    prob = problems.quadruped(60)
+    B = 16
+    rng = np.random.default_rng(5)
+    x = prob.x0[None, None] + 0.05 * rng.standard_normal((B, prob.N, 36))
+    x[B // 2:, :, 2] += 0.05                     # second half airborne
+    u = prob.u_guess.T[None] + 2.0 * rng.standard_normal((B, prob.N - 1, 12))
+    out = {}
+    for mode in ("ad", "structured"):
+        if mode == "structured":
+            monkeypatch.setenv("DDP_QUAD_STRUCTURED", "1")
+        s = make_gpu(prob, B=B)
+        s.put(_lib.X_BAR, x)
+        s.put(_lib.U_BAR, u)
+        s.run_phase(_lib.PHASE_DERIVATIVES)
+        out[mode] = (s.get(_lib.FX), s.get(_lib.FU))
+    assert relerr(out["structured"][0], out["ad"][0]) < 1e-12
+    assert relerr(out["structured"][1], out["ad"][1]) < 1e-12
+    o = make_oracle(prob)
+    for b in (0, B - 1):
+        for t in (0, 17, 58):
+            fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
+            assert np.abs(out["structured"][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max())
+            assert np.abs(out["structured"][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max())
