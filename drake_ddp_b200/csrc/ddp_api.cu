@@ -112,7 +112,7 @@ void carve(Dev& d, double** params, int np, Carver& c, int model, double** quadG
   *quadG = nullptr;
   *quadXmid = nullptr;
   *quadTab = nullptr;
-  if (model == MODEL_QUADRUPED) {
+  if (model == MODEL_QUADRUPED && getenv("DDP_QUAD_STRUCTURED")) {  // opt-in path only
     *quadG = c.take<double>(((B * T + 7) / 8) * 2 * 144 * 32);
     *quadXmid = c.take<double>(B * T * 2 * 36);
     *quadTab = c.take<unsigned long long>(kQuadTabSize);
@@ -198,7 +198,7 @@ int launch_quad_linearize(ddp_solver* s, const int* list, const int* count) {
   return 0;
 }
 int do_linearize(ddp_solver* s, const int* list, const int* count) {
-  if (s->model == MODEL_QUADRUPED && s->quad_sub > 0 && s->quad_structured)
+  if (s->model == MODEL_QUADRUPED && s->quad_sub > 0 && s->quad_structured && s->quadG)
     return launch_quad_linearize(s, list, count);
   DDP_MODEL_SWITCH(s->model, return launch_linearize<Model>(s, list, count));
   return 0;
