@@ -312,6 +312,21 @@ struct Quadruped {
   __device__ __forceinline__ static double pick4(int l, double a, double b, double c, double d) {
     return l == 0 ? a : (l == 1 ? b : (l == 2 ? c : d));
   }
+  // base_pose() with the three sincos pairs dealt to lanes 0..2 of the group and exchanged by
+  // shuffle: same values as the scalar version (same inputs, same function), a third of the trig.
+  __device__ __forceinline__ static void base_pose_coop(int lane, unsigned mask, int gbase, const double* q,
+                                                        BasePose<double>& B) {
+    double sn, cs;
+    sincos_(pick4(lane, q[3], q[4], q[5], q[5]), &sn, &cs);
+    B.sr = __shfl_sync(mask, sn, gbase + 0);
+    B.cr = __shfl_sync(mask, cs, gbase + 0);
+    B.sp = __shfl_sync(mask, sn, gbase + 1);
+    B.cp = __shfl_sync(mask, cs, gbase + 1);
+    const double sy = __shfl_sync(mask, sn, gbase + 2), cy = __shfl_sync(mask, cs, gbase + 2);
+    B.R00 = cy * B.cp; B.R01 = cy * B.sp * B.sr - sy * B.cr; B.R02 = cy * B.sp * B.cr + sy * B.sr;
+    B.R10 = sy * B.cp; B.R11 = sy * B.sp * B.sr + cy * B.cr; B.R12 = sy * B.sp * B.cr - cy * B.sr;
+    B.R20 = -B.sp; B.R21 = B.cp * B.sr; B.R22 = B.cp * B.cr;
+  }
   __device__ __forceinline__ static void step_coop(int lane, unsigned mask, int gbase, const double* x,
                                                    const double* u, double* xn, const double* p) {
     const int sub = (int)p[1];
@@ -328,7 +343,7 @@ struct Quadruped {
     const double sx = (lane < 2) ? 1.0 : -1.0, sd = (lane & 1) ? 1.0 : -1.0;
     for (int it = 0; it < sub; ++it) {
       BasePose<double> B;
-      base_pose(q, B);
+      base_pose_coop(lane, mask, gbase, q, B);
       LegOut<double> o;
       leg(sx, sd, pick4(lane, q[6], q[9], q[12], q[15]), pick4(lane, q[7], q[10], q[13], q[16]),
           pick4(lane, q[8], q[11], q[14], q[17]), pick4(lane, v[6], v[9], v[12], v[15]),
