@@ -263,27 +263,37 @@ struct Quadruped {
     acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) / Iz;
   }
 
-  // one semi-implicit Euler substep of length h, in place
+  // one semi-implicit Euler substep of length h, in place.  Leg loads are summed pairwise,
+  // (leg0 + leg1) + (leg2 + leg3), the association of the 4-lane butterfly in step_coop; only two
+  // legs' outputs are alive at a time to keep the dual-number instantiation in registers.
   template <class S>
   DDP_HD static void substep(S* q, S* v, const S* u, const double* p, double h) {
     BasePose<S> B;
     base_pose(q, B);
-    LegOut<S> o[4];
     S acc[18];
+    S sum[2][6];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      leg((l < 2) ? 1.0 : -1.0, (l & 1) ? 1.0 : -1.0, q[6 + 3 * l], q[7 + 3 * l], q[8 + 3 * l],
-          v[6 + 3 * l], v[7 + 3 * l], v[8 + 3 * l], u[3 * l], u[3 * l + 1], u[3 * l + 2], q[2], v, B, p,
-          o[l]);
-      acc[6 + 3 * l] = o[l].a0;
-      acc[7 + 3 * l] = o[l].a1;
-      acc[8 + 3 * l] = o[l].a2;
+    for (int pair = 0; pair < 2; ++pair) {
+      LegOut<S> o[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int l = 2 * pair + k;
+        leg((l < 2) ? 1.0 : -1.0, (l & 1) ? 1.0 : -1.0, q[6 + 3 * l], q[7 + 3 * l], q[8 + 3 * l],
+            v[6 + 3 * l], v[7 + 3 * l], v[8 + 3 * l], u[3 * l], u[3 * l + 1], u[3 * l + 2], q[2], v, B, p,
+            o[k]);
+        acc[6 + 3 * l] = o[k].a0;
+        acc[7 + 3 * l] = o[k].a1;
+        acc[8 + 3 * l] = o[k].a2;
+      }
+      sum[pair][0] = o[0].Fx + o[1].Fx;
+      sum[pair][1] = o[0].Fy + o[1].Fy;
+      sum[pair][2] = o[0].Fz + o[1].Fz;
+      sum[pair][3] = o[0].Tx + o[1].Tx;
+      sum[pair][4] = o[0].Ty + o[1].Ty;
+      sum[pair][5] = o[0].Tz + o[1].Tz;
     }
-    // pairwise sums (same association as the 4-lane butterfly in step_coop)
-    base_acc((o[0].Fx + o[1].Fx) + (o[2].Fx + o[3].Fx), (o[0].Fy + o[1].Fy) + (o[2].Fy + o[3].Fy),
-             (o[0].Fz + o[1].Fz) + (o[2].Fz + o[3].Fz), (o[0].Tx + o[1].Tx) + (o[2].Tx + o[3].Tx),
-             (o[0].Ty + o[1].Ty) + (o[2].Ty + o[3].Ty), (o[0].Tz + o[1].Tz) + (o[2].Tz + o[3].Tz), v, p,
-             acc);
+    base_acc(sum[0][0] + sum[1][0], sum[0][1] + sum[1][1], sum[0][2] + sum[1][2], sum[0][3] + sum[1][3],
+             sum[0][4] + sum[1][4], sum[0][5] + sum[1][5], v, p, acc);
     integrate(q, v, acc, B, h);
   }
 
