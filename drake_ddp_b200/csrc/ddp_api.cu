@@ -598,14 +598,6 @@ int ddp_solve(ddp_solver_t* s, int max_iters, int* iters_done) {
   return 0;
 }
 
-int ddp_iterate_async(ddp_solver_t* s) { return iterate_impl(s, false, true); }
-
-int ddp_sync(ddp_solver_t* s) {
-  CK(cudaStreamSynchronize(s->stream));
-  CK(cudaGetLastError());
-  return 0;
-}
-
 int ddp_run_phase(ddp_solver_t* s, int phase) {
   Dev& d = s->d;
   LAUNCH1(begin_iter_kernel, d, 1);

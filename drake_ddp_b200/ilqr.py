@@ -158,12 +158,6 @@ class BatchedILQR:
         _lib.check(self._L.ddp_iterate(self._h, ctypes.byref(n_active)), "ddp_iterate")
         return n_active.value
 
-    def iterate_async(self):
-        _lib.check(self._L.ddp_iterate_async(self._h), "ddp_iterate_async")
-
-    def sync(self):
-        _lib.check(self._L.ddp_sync(self._h), "ddp_sync")
-
     def solve(self, max_iters=0) -> int:
         it = ctypes.c_int()
         _lib.check(self._L.ddp_solve(self._h, int(max_iters), ctypes.byref(it)), "ddp_solve")

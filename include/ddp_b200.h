@@ -136,10 +136,6 @@ int ddp_mpc_shift(ddp_solver_t* s, int replan_steps);
 int ddp_begin_solve(ddp_solver_t* s);
 int ddp_iterate(ddp_solver_t* s, int* n_active);
 int ddp_solve(ddp_solver_t* s, int max_iters, int* iters_done);
-/* One iteration for ALL trajectories regardless of convergence, no host sync inside
- * (benchmark / fixed-iteration mode); line search limited to one round of A candidates. */
-int ddp_iterate_async(ddp_solver_t* s);
-int ddp_sync(ddp_solver_t* s);
 
 /* One phase only (teacher-forced tests). */
 int ddp_run_phase(ddp_solver_t* s, int phase);
