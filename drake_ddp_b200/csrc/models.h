@@ -23,6 +23,7 @@ enum ModelId {
   MODEL_CARTPOLE_WALL = 3,  // n=4  m=1   cart_pole_with_wall.py
   MODEL_QUADRUPED = 4,      // n=36 m=12  mini_cheetah-scale (Euler-angle base)
   MODEL_ARM_BALL = 5,       // n=27 m=7   kinova/panda-scale arm pushing a ball
+  MODEL_QUADRUPED_QUAT = 6, // n=37 m=12  the quadruped in the reference's quaternion layout
   MODEL_AFFINE_SIN_4_1 = 10,   // x+ = A x + B u + 0.01 sin x (test stub, any A,B)
   MODEL_AFFINE_SIN_6_2 = 11,
   MODEL_AFFINE_SIN_27_7 = 12,
@@ -385,6 +386,108 @@ struct Quadruped {
 };
 
 // ------------------------------------------------------------------------------
+// The same quadruped with a quaternion floating base, in the reference's state layout
+// (mini_cheetah.py:41-57: n = 37):
+//   q = [qw qx qy qz | px py pz | (abad hip knee) x {FR, FL, HR, HL}]            (19)
+//   v = [world angular velocity | world linear velocity | joint rates]           (18)
+// so x[4] is the base x position and x[22] the base x velocity, as the script assumes.
+// The rotation uses the normalised quaternion; the state itself is not renormalised.
+// Same parameter vector as Quadruped.
+struct QuadrupedQuat {
+  static constexpr int n = 37, m = 12, np = 20;
+  static constexpr int COOP = 1;
+  template <class S>
+  DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
+    typedef Quadruped Qd;
+    const int sub = (int)p[1];
+    const double h = p[0] / sub;
+    const double Ix = p[3], Iy = p[4], Iz = p[5];
+    S qt[4], pos[3], qj[12], w[3], vl[3], vj[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qt[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      pos[i] = x[4 + i];
+      w[i] = x[19 + i];
+      vl[i] = x[22 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      qj[i] = x[7 + i];
+      vj[i] = x[25 + i];
+    }
+    for (int it = 0; it < sub; ++it) {
+      // rotation matrix of the normalised quaternion (body -> world)
+      S nn = sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+      S a = qt[0] / nn, b = qt[1] / nn, c = qt[2] / nn, d = qt[3] / nn;
+      Qd::BasePose<S> B;
+      B.R00 = 1.0 - 2.0 * (c * c + d * d); B.R01 = 2.0 * (b * c - a * d); B.R02 = 2.0 * (b * d + a * c);
+      B.R10 = 2.0 * (b * c + a * d); B.R11 = 1.0 - 2.0 * (b * b + d * d); B.R12 = 2.0 * (c * d - a * b);
+      B.R20 = 2.0 * (b * d - a * c); B.R21 = 2.0 * (c * d + a * b); B.R22 = 1.0 - 2.0 * (b * b + c * c);
+      B.sr = S(0.0); B.cr = S(1.0); B.sp = S(0.0); B.cp = S(1.0);
+      // leg() wants v = [world linear velocity | BODY angular velocity]
+      S vloc[6];
+      vloc[0] = vl[0]; vloc[1] = vl[1]; vloc[2] = vl[2];
+      vloc[3] = B.R00 * w[0] + B.R10 * w[1] + B.R20 * w[2];
+      vloc[4] = B.R01 * w[0] + B.R11 * w[1] + B.R21 * w[2];
+      vloc[5] = B.R02 * w[0] + B.R12 * w[1] + B.R22 * w[2];
+      S aj[12], sum[2][6];
+#pragma unroll
+      for (int pair = 0; pair < 2; ++pair) {
+        Qd::LegOut<S> o[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int l = 2 * pair + k;
+          Qd::leg((l < 2) ? 1.0 : -1.0, (l & 1) ? 1.0 : -1.0, qj[3 * l], qj[3 * l + 1], qj[3 * l + 2], vj[3 * l],
+                  vj[3 * l + 1], vj[3 * l + 2], u[3 * l], u[3 * l + 1], u[3 * l + 2], pos[2], vloc, B, p, o[k]);
+          aj[3 * l] = o[k].a0;
+          aj[3 * l + 1] = o[k].a1;
+          aj[3 * l + 2] = o[k].a2;
+        }
+        sum[pair][0] = o[0].Fx + o[1].Fx; sum[pair][1] = o[0].Fy + o[1].Fy; sum[pair][2] = o[0].Fz + o[1].Fz;
+        sum[pair][3] = o[0].Tx + o[1].Tx; sum[pair][4] = o[0].Ty + o[1].Ty; sum[pair][5] = o[0].Tz + o[1].Tz;
+      }
+      // body-frame Euler equations, then back to the world frame: wdot_W = R wdot_B
+      S Tx = sum[0][3] + sum[1][3], Ty = sum[0][4] + sum[1][4], Tz = sum[0][5] + sum[1][5];
+      S ab0 = (Tx - (Iz - Iy) * vloc[4] * vloc[5]) / Ix;
+      S ab1 = (Ty - (Ix - Iz) * vloc[5] * vloc[3]) / Iy;
+      S ab2 = (Tz - (Iy - Ix) * vloc[3] * vloc[4]) / Iz;
+      w[0] = w[0] + h * (B.R00 * ab0 + B.R01 * ab1 + B.R02 * ab2);
+      w[1] = w[1] + h * (B.R10 * ab0 + B.R11 * ab1 + B.R12 * ab2);
+      w[2] = w[2] + h * (B.R20 * ab0 + B.R21 * ab1 + B.R22 * ab2);
+      vl[0] = vl[0] + h * ((sum[0][0] + sum[1][0]) / p[2]);
+      vl[1] = vl[1] + h * ((sum[0][1] + sum[1][1]) / p[2]);
+      vl[2] = vl[2] + h * ((sum[0][2] + sum[1][2]) / p[2] - p[19]);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) vj[i] = vj[i] + h * aj[i];
+      // qdot = 0.5 * (0, w_W) (x) q
+      S q0 = qt[0], q1 = qt[1], q2 = qt[2], q3 = qt[3];
+      qt[0] = q0 + (0.5 * h) * (-(w[0] * q1) - w[1] * q2 - w[2] * q3);
+      qt[1] = q1 + (0.5 * h) * (w[0] * q0 + w[1] * q3 - w[2] * q2);
+      qt[2] = q2 + (0.5 * h) * (w[1] * q0 + w[2] * q1 - w[0] * q3);
+      qt[3] = q3 + (0.5 * h) * (w[2] * q0 + w[0] * q2 - w[1] * q1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pos[i] = pos[i] + h * vl[i];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) qj[i] = qj[i] + h * vj[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = qt[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      xn[4 + i] = pos[i];
+      xn[19 + i] = w[i];
+      xn[22 + i] = vl[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      xn[7 + i] = qj[i];
+      xn[25 + i] = vj[i];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------
 // Arm pushing a ball on a table, kinova_gen3 / panda_fr3 scale (7 + 7 + 13):
 //   q = [7 joint angles | ball quaternion (w x y z) | ball position]   (14)
 //   v = [7 joint rates  | ball angular velocity (world) | ball linear velocity] (13)
@@ -577,6 +680,7 @@ struct AffineSin {
     case ::ddp::MODEL_CARTPOLE_WALL: { typedef ::ddp::CartPoleWall Model; CALL; } break;  \
     case ::ddp::MODEL_QUADRUPED: { typedef ::ddp::Quadruped Model; CALL; } break;         \
     case ::ddp::MODEL_ARM_BALL: { typedef ::ddp::ArmBall Model; CALL; } break;            \
+    case ::ddp::MODEL_QUADRUPED_QUAT: { typedef ::ddp::QuadrupedQuat Model; CALL; } break; \
     case ::ddp::MODEL_AFFINE_SIN_4_1: { typedef ::ddp::AffineSin<4, 1> Model; CALL; } break;     \
     case ::ddp::MODEL_AFFINE_SIN_6_2: { typedef ::ddp::AffineSin<6, 2> Model; CALL; } break;     \
     case ::ddp::MODEL_AFFINE_SIN_27_7: { typedef ::ddp::AffineSin<27, 7> Model; CALL; } break;   \

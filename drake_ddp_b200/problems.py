@@ -134,6 +134,30 @@ def quadruped(N: int = 200, target_vel: float = 1.0, keypoints=None) -> Problem:
                    extra={"u_stand": u_stand, "target_vel": target_vel})
 
 
+def quadruped_quat(N: int = 50, target_vel: float = 1.0, keypoints=None) -> Problem:
+    """mini_cheetah.py:22-69,147-180 in the script's own n=37 layout and horizon (T=0.2, dt=4e-3
+    -> N=50): q = [quat, pos, joints], v = [omega, v, joint rates]; x_nom[4] += v*T, x_nom[22] += v."""
+    sysm = systems.quadruped_quat(dt=4e-3)
+    dt = sysm.dt
+    q18, u_stand = quadruped_stand(sysm)
+    q0 = np.hstack([[1.0, 0.0, 0.0, 0.0], q18[0:3], q18[6:18]])      # mini_cheetah.py:41-46
+    x0 = np.hstack([q0, np.zeros(18)])
+    x_nom = x0.copy()
+    x_nom[4] += target_vel * (N * dt)     # base x position   (mini_cheetah.py:56)
+    x_nom[22] += target_vel               # base x velocity   (mini_cheetah.py:57)
+    Qq_base = np.ones(7)
+    Qq_base[0:4] += 2                     # mini_cheetah.py:60-61
+    Qv_base = np.ones(6)
+    Qq_legs, Qv_legs = 0.0 * np.ones(12), 0.01 * np.ones(12)
+    Q = np.diag(np.hstack([Qq_base, Qq_legs, 0.01 * Qv_base, Qv_legs]))          # :66
+    R = 0.01 * np.eye(12)
+    Qf = np.diag(np.hstack([5 * Qq_base, 0.1 + Qq_legs, Qv_base, Qv_legs]))      # :68
+    u_guess = np.repeat(u_stand[:, None], N - 1, axis=1)
+    return Problem("quadruped_quat", sysm, N, x0, x_nom, dt * Q, dt * R, Qf, u_guess, beta=0.5,
+                   delta=1e-2, gamma=0.0, keypoints=keypoints, sigma=0.002,
+                   extra={"u_stand": u_stand, "target_vel": target_vel})
+
+
 # ---- arm + ball (kinova_gen3 / panda_fr3-scale) --------------------------------------
 def arm_tip(sysm: systems.AnalyticSystem, q_arm):
     """Tool-tip position of the 7R chain of csrc/models.h ArmBall (z, y, z, y, z, y, z axes;

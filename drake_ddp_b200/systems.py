@@ -21,6 +21,7 @@ MODEL_CARTPOLE = 2
 MODEL_CARTPOLE_WALL = 3
 MODEL_QUADRUPED = 4
 MODEL_ARM_BALL = 5
+MODEL_QUADRUPED_QUAT = 6
 MODEL_AFFINE_SIN = {(4, 1): 10, (6, 2): 11, (27, 7): 12, (36, 12): 13, (37, 12): 14}
 
 
@@ -91,6 +92,13 @@ def quadruped(dt=4e-3, substeps=2, mass=8.252, inertia=(0.07, 0.26, 0.242),
     p = [dt, float(substeps), mass, *inertia, *joint_inertia, joint_damping, l_abad, l_thigh,
          l_shank, hip_x, hip_y, foot_radius, modulus, mu, v_stiction, g]
     return AnalyticSystem("quadruped", MODEL_QUADRUPED, 36, 12, np.array(p, dtype=np.float64))
+
+
+def quadruped_quat(**kw) -> AnalyticSystem:
+    """The quadruped with a quaternion floating base in the reference's n=37 state layout
+    (mini_cheetah.py:41-57); same parameters as ``quadruped``."""
+    base = quadruped(**kw)
+    return AnalyticSystem("quadruped_quat", MODEL_QUADRUPED_QUAT, 37, 12, base.params)
 
 
 def arm_ball(dt=1e-2, substeps=4, joint_inertia=0.3, joint_damping=0.5,

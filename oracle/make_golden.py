@@ -39,6 +39,7 @@ CASES = {
     "arm_ball_N40_setInterval5": (lambda: problems.arm_ball(40),
                                   derivs_interpolation("setInterval", 5, 40, 1e-4, 1e-2), 2),
     "quadruped_N30": (lambda: problems.quadruped(30), None, 3),
+    "quadruped_quat_N30": (lambda: problems.quadruped_quat(30), None, 3),
     "quadruped_N30_adaptiveJerk": (lambda: problems.quadruped(30),
                                    derivs_interpolation("adaptiveJerk", 2, 20, 0.3, 10), 3),
 }

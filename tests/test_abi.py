@@ -35,7 +35,8 @@ def test_every_declared_symbol_is_exported(L):
 
 def test_model_dims(L):
     for prob in (problems.pendulum(), problems.acrobot(), problems.cart_pole(), problems.cart_pole_with_wall(),
-                 problems.quadruped(), problems.arm_ball(), problems.affine_sin(37, 12, 10)):
+                 problems.quadruped(), problems.quadruped_quat(), problems.arm_ball(),
+                 problems.affine_sin(37, 12, 10)):
         n, m, npar = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         assert L.ddp_model_dims(prob.system.model_id, ctypes.byref(n), ctypes.byref(m), ctypes.byref(npar)) == 0
         assert (n.value, m.value, npar.value) == (prob.system.n, prob.system.m, prob.system.params.size)

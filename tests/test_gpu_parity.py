@@ -61,6 +61,7 @@ PER_ITER = [
     ("affine_36_12_jerk", lambda: problems.affine_sin(36, 12, 40), derivs_interpolation("adaptiveJerk", 2, 10, 1e-4, 0), 3),
     ("affine_27_7_ie", lambda: problems.affine_sin(27, 7, 40), derivs_interpolation("iterativeError", 2, 0, 0, 1e-9), 3),
     ("quadruped", lambda: problems.quadruped(50), None, 4),
+    ("quadruped_quat_n37", lambda: problems.quadruped_quat(50), None, 4),
     ("quadruped_interval", lambda: problems.quadruped(50), derivs_interpolation("setInterval", 4, 0, 0, 0), 3),
     ("quadruped_ie", lambda: problems.quadruped(40), derivs_interpolation("iterativeError", 2, 0, 0, 1e-7), 3),
 ]

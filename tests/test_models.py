@@ -51,7 +51,8 @@ def test_host_model_matches_numpy_restatement(sysm, fn):
         np.testing.assert_allclose(dyn.step(x, u), fn(x, u, sysm.params), rtol=1e-12, atol=1e-13)
 
 
-@pytest.mark.parametrize("name", ["pendulum", "acrobot", "cart_pole", "cart_pole_with_wall", "quadruped", "arm_ball"])
+@pytest.mark.parametrize("name", ["pendulum", "acrobot", "cart_pole", "cart_pole_with_wall", "quadruped",
+                                  "quadruped_quat", "arm_ball"])
 def test_jacobian_matches_central_differences(name):
     prob = getattr(problems, name)()
     dyn = HostDynamics(prob.system)
@@ -109,3 +110,23 @@ def test_pendulum_energy_without_damping():
     for _ in range(2000):
         x = dyn.step(x, [0.0])
     assert abs(energy(x) - e0) < 2e-2 * abs(e0)   # symplectic Euler: bounded energy error
+
+
+def test_quaternion_and_euler_quadrupeds_agree():
+    """The n=37 quaternion-base model (reference layout) and the n=36 Euler-angle model are the same
+    physics: identical torques give the same base/joint motion up to the O(h^2) difference of the
+    two attitude integrators."""
+    p37, p36 = problems.quadruped_quat(50), problems.quadruped(50)
+    d37, d36 = HostDynamics(p37.system), HostDynamics(p36.system)
+    rng = np.random.default_rng(0)
+    xa, xb = p37.x0.copy(), p36.x0.copy()
+    for _ in range(30):
+        u = p37.extra["u_stand"] + 0.5 * rng.standard_normal(12)
+        xa, xb = d37.step(xa, u), d36.step(xb, u)
+    assert np.abs(xa[4:7] - xb[0:3]).max() < 1e-6          # base position
+    assert np.abs(xa[7:19] - xb[6:18]).max() < 1e-6        # joints
+    qw, qx, qy, qz = xa[:4] / np.linalg.norm(xa[:4])
+    rpy = [np.arctan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy)), np.arcsin(2 * (qw * qy - qz * qx)),
+           np.arctan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz))]
+    assert np.abs(np.array(rpy) - xb[3:6]).max() < 1e-6
+    assert p37.system.n == 37 and p37.x_nom[4] > p37.x0[4] and p37.x_nom[22] == 1.0   # mini_cheetah.py:56-57
