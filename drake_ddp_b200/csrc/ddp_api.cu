@@ -96,6 +96,7 @@ void carve(Dev& d, double** params, int np, Carver& c, int model, double** quadG
   d.acc = c.take<int>(B);
   d.iters = c.take<int>(B);
   d.counters = c.take<int>(4);
+  d.sm_slots = c.take<int>(1024);
   d.unres = c.take<int>(B);
   d.kplist = c.take<int>(B * T);
   d.kpcount = c.take<int>(B);
@@ -695,5 +696,18 @@ int ddp_peak_fp64(void* stream, int use_mma, double* tflops) {
   CK(cudaEventDestroy(e1));
   return 0;
 }
+
+#ifdef DDP_BWD_PROFILE
+// debug builds only: per-phase cycle totals recorded by backward_mma_kernel
+int ddp_debug_bwd_profile(long long* out64) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out64, ddp::g_bwd_prof, sizeof(long long) * 64));
+  int fb = 0, zero = 0;
+  CK(cudaMemcpyFromSymbol(&fb, ddp::g_bwd_fallbacks, sizeof(int)));
+  CK(cudaMemcpyToSymbol(ddp::g_bwd_fallbacks, &zero, sizeof(int)));
+  out64[63] = fb;
+  return 0;
+}
+#endif
 
 }  // extern "C"
