@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,7 @@
 #include "kernels.cuh"
 #include "backward_mma.cuh"
 #include "quadruped_linearize.cuh"
+#include "quadruped_fused.cuh"
 
 using namespace ddp;
 
@@ -38,7 +40,8 @@ struct ddp_solver {
   long long launches;
   bool timings_valid;
   bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
-  bool quad_structured;  // opt-in (DDP_QUAD_STRUCTURED=1): structured quadruped linearization
+  bool quad_structured;  // opt-in (DDP_QUAD_STRUCTURED=1): two-kernel structured quadruped linearization
+  bool quad_fused;       // fused structured quadruped linearization (DDP_QUAD_LINEARIZE=fused|ad)
   double* quadG;         // quadruped fast path: local leg Jacobians [B*T][sub][4][144]
   double* quadXmid;      //                      state after each substep [B*T][sub][36]
   int quad_sub;          // substeps of the quadruped model (0: fast path unavailable)
@@ -198,7 +201,29 @@ int launch_quad_linearize(ddp_solver* s, const int* list, const int* count) {
   s->launches++;
   return 0;
 }
+int launch_quad_fused(ddp_solver* s, const int* list, const int* count) {
+  const size_t smem = sizeof(QfWarpSmem) * kQfWarps;
+  static int ctas = 0;
+  if (!ctas) {
+    cudaError_t e = cudaFuncSetAttribute(quad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_err = std::string("cudaFuncSetAttribute(quad_fused): ") + cudaGetErrorString(e);
+      return DDP_ERR_CUDA;
+    }
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quad_fused_kernel, kQfWarps * 32, smem);
+    ctas = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int n_items = s->d.B * s->d.T;
+  const int grid = std::min(ctas, cdiv(n_items, kQfWarps));
+  quad_fused_kernel<<<grid, kQfWarps * 32, smem, s->stream>>>(s->d, list, count, n_items);
+  s->launches++;
+  return 0;
+}
 int do_linearize(ddp_solver* s, const int* list, const int* count) {
+  if (s->model == MODEL_QUADRUPED && s->quad_sub == 2 && s->quad_fused) return launch_quad_fused(s, list, count);
   if (s->model == MODEL_QUADRUPED && s->quad_sub > 0 && s->quad_structured && s->quadG)
     return launch_quad_linearize(s, list, count);
   DDP_MODEL_SWITCH(s->model, return launch_linearize<Model>(s, list, count));
@@ -416,6 +441,10 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
     if (sub == 1 || sub == 2) s->quad_sub = sub;
   }
   s->quad_structured = getenv("DDP_QUAD_STRUCTURED") != nullptr;
+  {
+    const char* mode = getenv("DDP_QUAD_LINEARIZE");
+    s->quad_fused = !s->quad_structured && mode && std::string(mode) == "fused";
+  }
   d.params = params;
   CK(cudaMemsetAsync(workspace_dev, 0, c.off, s->stream));
   CK(cudaMemcpyAsync(params, params_host, np * sizeof(double), cudaMemcpyHostToDevice, s->stream));

@@ -1,0 +1,270 @@
+// K4 for the quadruped model: structured linearization fused into one kernel.
+//
+// Replaces _calc_dynamics_partials (/root/reference/ilqr.py:233-272) over the keypoints
+// (:409-411) for Quadruped::step (models.h).  The generic linearize_kernel pushes all n+m = 48
+// seed directions through both substeps (4 legs x 48 directions x 2 substeps = 384 dual leg
+// evaluations per point).  A leg's loads depend on 16 local inputs only (base height and
+// attitude, base twist, its own three joints and rates), so here
+//   1. per substep, the 4 x 16 (leg, local direction) pairs are dealt to the 32 lanes of a warp,
+//      two directions per lane, and Quadruped::leg is evaluated with Dual<2>: the same
+//      templates as the rollout, 64 dual leg evaluations per substep instead of 192;
+//   2. every lane scatters its derivatives straight into the substep Jacobian in shared memory
+//      (base rows are summed over the legs with the same two-stage butterfly the rollout uses),
+//      the integrator rows follow element-wise (QuadJac::dq_elem);
+//   3. the two substeps are chained on the fp64 tensor pipe: only the velocity rows need a
+//      product, v2 = Dv2[:, :36] D1 + [0 | Dv2[:, 36:]] (162 DMMAs), the position rows follow
+//      from q+ = q + h N(q) v+ element-wise.
+// One warp per point, all intermediates in that warp's slice of shared memory; fx, fu are
+// written once.  Exact derivative of Quadruped::step: checked against the generic AD kernel
+// and the host AD (tests/test_gpu_parity.py).  Two substeps only (the model's setting); other
+// settings use the generic kernel.
+#pragma once
+#include "backward_mma.cuh"
+#include "quadruped_jac.h"
+
+namespace ddp {
+
+constexpr int kQfLd = 52;     // leading dimension of the Jacobians in shared memory (52 = 4 mod 16:
+                              // conflict-free 8 x 4 and 4 x 8 DMMA operand fetches)
+constexpr int kQfWarps = 4;   // warps (points in flight) per CTA
+
+struct QfWarpSmem {
+  double D1[36 * kQfLd];      // substep-1 Jacobian d(q1, v1)/d(q, v, u), 36 x 48
+  double D2v[18 * kQfLd];     // velocity rows of the substep-2 Jacobian, 18 x 48
+  double v2s[3 * 48];         // rows 3..5 of the chained velocity rows (Euler-rate coupling)
+  double st[3][36];           // x_t, state after substep 1, after substep 2
+};
+
+__global__ void __launch_bounds__(kQfWarps * 32, 2)
+quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
+  typedef Quadruped Qd;
+  typedef Dual<2> D2;
+  constexpr int LD = kQfLd;
+  extern __shared__ __align__(16) unsigned char qf_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  QfWarpSmem& s = reinterpret_cast<QfWarpSmem*>(qf_raw)[warp];
+  const unsigned full = 0xffffffffu;
+  const double* p = d.params;
+  const double h = p[0] / 2.0;
+  const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5];
+  const int T = d.T;
+
+  // lane -> (leg, pair of local directions) and the global columns of the two directions
+  const int leg = lane >> 3, dp = lane & 7;
+  const int j0 = 2 * dp, j1 = j0 + 1;
+  const int gc[2] = {QuadJac::gcol(leg, j0), QuadJac::gcol(leg, j1)};
+  const bool shared_dir = dp < 5;   // base directions: every leg contributes to the base rows
+  const double sx = (leg < 2) ? 1.0 : -1.0, sd = (leg & 1) ? 1.0 : -1.0;
+
+  // the Jacobian buffers keep their zero pattern across points: only the structural nonzeros
+  // are rewritten.  The direct u -> joint acceleration terms are constant.
+  for (int i = lane; i < 36 * LD; i += 32) s.D1[i] = 0.0;
+  for (int i = lane; i < 18 * LD; i += 32) s.D2v[i] = 0.0;
+  __syncwarp();
+  if (lane < 12) {
+    s.D1[(18 + 6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
+    s.D2v[(6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
+  }
+  __syncwarp();
+
+  for (int item = blockIdx.x * kQfWarps + warp; item < n_items; item += gridDim.x * kQfWarps) {
+    const int b = item / T, i = item % T;
+    if (!d.active[b] || i >= count[b]) continue;
+    const int t = list[(size_t)b * T + i];
+    const size_t bt = (size_t)b * T + t;
+    const double* up = d.u_bar + bt * 12;
+    for (int k = lane; k < 36; k += 32) s.st[0][k] = d.x_bar[((size_t)b * d.N + t) * 36 + k];
+    const double ua = up[3 * leg], uh = up[3 * leg + 1], uk = up[3 * leg + 2];
+    __syncwarp();
+
+    double trig[2][4];   // sin/cos of roll and pitch at the start of each substep
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const double* xin = s.st[sub];
+      double* xout = s.st[sub + 1];
+      double* Dv = (sub == 0) ? (s.D1 + 18 * LD) : s.D2v;   // 18 x 48 velocity rows of this substep
+      // ---- dual evaluation of this lane's leg along its two local directions -----------------
+      auto seed = [&](double v, int j) {
+        D2 r;
+        r.v = v;
+        r.d[0] = (j == j0) ? 1.0 : 0.0;
+        r.d[1] = (j == j1) ? 1.0 : 0.0;
+        return r;
+      };
+      D2 qb[6], vb[6];
+      qb[0] = D2(0.0); qb[1] = D2(0.0);
+      qb[2] = seed(xin[2], 0);
+      qb[3] = seed(xin[3], 1);
+      qb[4] = seed(xin[4], 2);
+      qb[5] = seed(xin[5], 3);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vb[k] = seed(xin[18 + k], 4 + k);
+      Qd::BasePose<D2> B;
+      Qd::base_pose(qb, B);
+      trig[sub][0] = B.sr.v; trig[sub][1] = B.cr.v; trig[sub][2] = B.sp.v; trig[sub][3] = B.cp.v;
+      Qd::LegOut<D2> o;
+      Qd::leg(sx, sd, seed(xin[6 + 3 * leg], 10), seed(xin[7 + 3 * leg], 11), seed(xin[8 + 3 * leg], 12),
+              seed(xin[24 + 3 * leg], 13), seed(xin[25 + 3 * leg], 14), seed(xin[26 + 3 * leg], 15), D2(ua), D2(uh),
+              D2(uk), qb[2], vb, B, p, o);
+      // ---- scatter: joint rows of this leg, base rows summed over the legs ---------------------
+      {
+        const D2* ja[3] = {&o.a0, &o.a1, &o.a2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int r = 6 + 3 * leg + k;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) Dv[r * LD + gc[e]] = h * ja[k]->d[e] + ((gc[e] == 18 + r) ? 1.0 : 0.0);
+        }
+        const D2* fo[6] = {&o.Fx, &o.Fy, &o.Fz, &o.Tx, &o.Ty, &o.Tz};
+        const double inv[6] = {1.0 / mass, 1.0 / mass, 1.0 / mass, 1.0 / Ix, 1.0 / Iy, 1.0 / Iz};
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            double own = fo[r]->d[e], sum = own;
+            sum += __shfl_xor_sync(full, sum, 8);
+            sum += __shfl_xor_sync(full, sum, 16);
+            const double gs = shared_dir ? sum : own;
+            if (!shared_dir || leg == 0) Dv[r * LD + gc[e]] = (h * inv[r]) * gs + ((gc[e] == 18 + r) ? 1.0 : 0.0);
+          }
+        }
+      }
+      // ---- primal state after the substep (same arithmetic as Quadruped::integrate) ------------
+      double f[6] = {o.Fx.v, o.Fy.v, o.Fz.v, o.Tx.v, o.Ty.v, o.Tz.v};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        f[k] += __shfl_xor_sync(full, f[k], 8);
+        f[k] += __shfl_xor_sync(full, f[k], 16);
+      }
+      double vcur[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vcur[k] = vb[k].v;
+      double accb[18];
+      Qd::base_acc(f[0], f[1], f[2], f[3], f[4], f[5], vcur, p, accb);
+      {
+        const int jl = (lane >= 6 && lane < 18) ? (lane - 6) / 3 : 0, jk = (lane >= 6 && lane < 18) ? (lane - 6) % 3 : 0;
+        const double a0 = __shfl_sync(full, o.a0.v, 8 * jl), a1 = __shfl_sync(full, o.a1.v, 8 * jl),
+                     a2 = __shfl_sync(full, o.a2.v, 8 * jl);
+        double acc = (jk == 0) ? a0 : ((jk == 1) ? a1 : a2);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (lane == k) acc = accb[k];
+        const int li = (lane < 18) ? lane : 0;
+        const double vnew = xin[18 + li] + h * acc;
+        const double w3 = __shfl_sync(full, vnew, 3), w4 = __shfl_sync(full, vnew, 4), w5 = __shfl_sync(full, vnew, 5);
+        const double sr = trig[sub][0], cr = trig[sub][1], sp = trig[sub][2], cp = trig[sub][3];
+        const double tp = sp / cp, wyz = sr * w4 + cr * w5;
+        double rate = vnew;
+        if (lane == 3) rate = w3 + tp * wyz;
+        if (lane == 4) rate = cr * w4 - sr * w5;
+        if (lane == 5) rate = wyz / cp;
+        if (lane < 18) {
+          xout[18 + lane] = vnew;
+          xout[lane] = xin[lane] + h * rate;
+        }
+      }
+      __syncwarp();
+      // gyroscopic terms of the base rotation rows (d/d omega of the omega x I omega term)
+      if (lane < 6) {
+        const int rr = 3 + lane / 2;
+        const int cc = (lane == 0) ? 22 : (lane == 1) ? 23 : (lane == 2) ? 23 : (lane == 3) ? 21 : (lane == 4) ? 21 : 22;
+        const double w3 = xin[21], w4 = xin[22], w5 = xin[23];
+        const double val = (lane == 0)   ? -h * (Iz - Iy) * w5 / Ix
+                           : (lane == 1) ? -h * (Iz - Iy) * w4 / Ix
+                           : (lane == 2) ? -h * (Ix - Iz) * w3 / Iy
+                           : (lane == 3) ? -h * (Ix - Iz) * w5 / Iy
+                           : (lane == 4) ? -h * (Iy - Ix) * w4 / Iz
+                                         : -h * (Iy - Ix) * w3 / Iz;
+        Dv[rr * LD + cc] += val;
+      }
+      __syncwarp();
+      if (sub == 0) {
+        // position rows of D1 from its finished velocity rows (QuadJac::dq_elem)
+        for (int r = 0; r < 18; ++r)
+          for (int c = lane; c < 48; c += 32)
+            s.D1[r * LD + c] = QuadJac::dq_elem(s.D1 + 18 * LD, LD, trig[0][0], trig[0][1], trig[0][2], trig[0][3],
+                                                xout + 18, h, r, c);
+        __syncwarp();
+      }
+    }
+
+    // ---- chain: v2 = Dv2[:, :36] D1 + [0 | Dv2[:, 36:]] on the tensor pipe -----------------------
+    double acc[3][6][2];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    {
+      const double* pa[3];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) pa[mt] = s.D2v + min(8 * mt + g, 17) * LD + tg;
+      const double* pb = s.D1 + tg * LD + g;
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk) {
+        double a[3], bb[6];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) a[mt] = pa[mt][4 * kk];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) bb[nt] = pb[4 * kk * LD + 8 * nt];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 6; ++nt) dmma(acc[mt][nt], a[mt], bb[nt]);
+      }
+    }
+    double* fx = d.fx + bt * 36 * 36;
+    double* fu = d.fu + bt * 36 * 12;
+    auto store2 = [&](int r, int c, double v0, double v1) {   // rows of [fx | fu], c even
+      if (c < 36) *reinterpret_cast<double2*>(fx + r * 36 + c) = make_double2(v0, v1);
+      else *reinterpret_cast<double2*>(fu + r * 12 + (c - 36)) = make_double2(v0, v1);
+    };
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+      const int r = 8 * mt + g;
+      if (r < 18) {
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          const int c = 8 * nt + 2 * tg;
+          double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+          if (c >= 36) {
+            v0 += s.D2v[r * LD + c];
+            v1 += s.D2v[r * LD + c + 1];
+          }
+          store2(18 + r, c, v0, v1);
+          if (r >= 3 && r < 6) {   // Euler-rate rows need rows 3..5 together: stage them
+            s.v2s[(r - 3) * 48 + c] = v0;
+            s.v2s[(r - 3) * 48 + c + 1] = v1;
+          } else {                 // q+ = q + h v+
+            store2(r, c, s.D1[r * LD + c] + h * v0, s.D1[r * LD + c + 1] + h * v1);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    {
+      // rows 3..5: q2 = (I + h M2) D1q + h N2 v2 with the Euler-rate matrices of substep 2
+      const double sr = trig[1][0], cr = trig[1][1], sp = trig[1][2], cp = trig[1][3];
+      const double tp = sp / cp, wy = s.st[2][22], wz = s.st[2][23];
+      const double wyz = sr * wy + cr * wz, wr = cr * wy - sr * wz;
+      for (int c = lane; c < 48; c += 32) {
+        const double d3 = s.D1[3 * LD + c], d4 = s.D1[4 * LD + c], d5 = s.D1[5 * LD + c];
+        const double e3 = s.v2s[c], e4 = s.v2s[48 + c], e5 = s.v2s[96 + c];
+        const double q3 = (1.0 + h * tp * wr) * d3 + (h * wyz / (cp * cp)) * d4 + h * (e3 + tp * (sr * e4 + cr * e5));
+        const double q4 = (-h * wyz) * d3 + d4 + h * (cr * e4 - sr * e5);
+        const double q5 = (h * wr / cp) * d3 + (h * wyz * sp / (cp * cp)) * d4 + d5 + h * ((sr * e4 + cr * e5) / cp);
+        if (c < 36) {
+          fx[3 * 36 + c] = q3;
+          fx[4 * 36 + c] = q4;
+          fx[5 * 36 + c] = q5;
+        } else {
+          fu[3 * 12 + c - 36] = q3;
+          fu[4 * 12 + c - 36] = q4;
+          fu[5 * 12 + c - 36] = q5;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace ddp

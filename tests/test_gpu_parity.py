@@ -315,9 +315,11 @@ def test_full_size_c4_properties():
 
 
 def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
-    """The opt-in structured quadruped linearization (closed-form leg Jacobians + DMMA chain,
-    csrc/quadruped_linearize.cuh, DDP_QUAD_STRUCTURED=1) against the default forward-mode-AD
-    kernel on the same points, in contact and in flight."""
+    """The structured quadruped linearizations -- the fused kernel (dual leg evaluation along the
+    16 local directions + DMMA chain, csrc/quadruped_fused.cuh, DDP_QUAD_LINEARIZE=fused) and the
+    older two-kernel variant (closed-form leg Jacobians, csrc/quadruped_linearize.cuh,
+    DDP_QUAD_STRUCTURED=1) -- against the generic forward-mode-AD kernel on the same points, in
+    contact and in flight, and against the host AD."""
     prob = problems.quadruped(60)
     B = 16
     rng = np.random.default_rng(5)
@@ -325,7 +327,9 @@ def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
     x[B // 2:, :, 2] += 0.05                     # second half airborne
     u = prob.u_guess.T[None] + 2.0 * rng.standard_normal((B, prob.N - 1, 12))
     out = {}
-    for mode in ("ad", "structured"):
+    for mode in ("ad", "structured", "fused"):
+        monkeypatch.delenv("DDP_QUAD_STRUCTURED", raising=False)
+        monkeypatch.setenv("DDP_QUAD_LINEARIZE", "fused" if mode == "fused" else "ad")
         if mode == "structured":
             monkeypatch.setenv("DDP_QUAD_STRUCTURED", "1")
         s = make_gpu(prob, B=B)
@@ -333,11 +337,12 @@ def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
         s.put(_lib.U_BAR, u)
         s.run_phase(_lib.PHASE_DERIVATIVES)
         out[mode] = (s.get(_lib.FX), s.get(_lib.FU))
-    assert relerr(out["structured"][0], out["ad"][0]) < 1e-12
-    assert relerr(out["structured"][1], out["ad"][1]) < 1e-12
     o = make_oracle(prob)
-    for b in (0, B - 1):
-        for t in (0, 17, 58):
-            fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
-            assert np.abs(out["structured"][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max())
-            assert np.abs(out["structured"][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max())
+    for mode in ("structured", "fused"):
+        assert relerr(out[mode][0], out["ad"][0]) < 1e-12, mode
+        assert relerr(out[mode][1], out["ad"][1]) < 1e-12, mode
+        for b in (0, B - 1):
+            for t in (0, 17, 58):
+                fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
+                assert np.abs(out[mode][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max()), mode
+                assert np.abs(out[mode][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max()), mode
