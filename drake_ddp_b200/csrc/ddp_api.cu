@@ -442,8 +442,9 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   }
   s->quad_structured = getenv("DDP_QUAD_STRUCTURED") != nullptr;
   {
+    // default: the fused structured kernel; DDP_QUAD_LINEARIZE=ad selects the generic AD kernel
     const char* mode = getenv("DDP_QUAD_LINEARIZE");
-    s->quad_fused = !s->quad_structured && mode && std::string(mode) == "fused";
+    s->quad_fused = !s->quad_structured && !(mode && std::string(mode) == "ad");
   }
   d.params = params;
   CK(cudaMemsetAsync(workspace_dev, 0, c.off, s->stream));

@@ -177,6 +177,11 @@ struct Quadruped {
     sincos_(q[3], &B.sr, &B.cr);
     sincos_(q[4], &B.sp, &B.cp);
     sincos_(q[5], &sy, &cy);
+    base_pose_trig(sy, cy, B);
+  }
+  // rotation matrix from the sines / cosines (B.sr, B.cr, B.sp, B.cp already set)
+  template <class S>
+  DDP_HD static void base_pose_trig(const S& sy, const S& cy, BasePose<S>& B) {
     // R = Rz(yaw) Ry(pitch) Rx(roll), body -> world
     B.R00 = cy * B.cp; B.R01 = cy * B.sp * B.sr - sy * B.cr; B.R02 = cy * B.sp * B.cr + sy * B.sr;
     B.R10 = sy * B.cp; B.R11 = sy * B.sp * B.sr + cy * B.cr; B.R12 = sy * B.sp * B.cr - cy * B.sr;
@@ -188,12 +193,21 @@ struct Quadruped {
   DDP_HD static void leg(double sx, double sd, const S& qa, const S& qh, const S& qk, const S& va,
                          const S& vh, const S& vk, const S& ua, const S& uh, const S& uk, const S& pz,
                          const S* v, const BasePose<S>& B, const double* p, LegOut<S>& o) {
-    const double bj = p[9], l1 = p[10], l2 = p[11], l3 = p[12];
-    const double hx = p[13], hy = p[14], rf = p[15], E = p[16], mu = p[17], vs = p[18];
     S sa, ca, sh, ch, sk, ck;
     sincos_(qa, &sa, &ca);
     sincos_(qh, &sh, &ch);
     sincos_(qh + qk, &sk, &ck);
+    leg_trig(sx, sd, sa, ca, sh, ch, sk, ck, va, vh, vk, ua, uh, uk, pz, v, B, p, o);
+  }
+  // the same with the sines / cosines of abad, hip and hip + knee supplied by the caller (the
+  // fused linearization computes each of them once per warp)
+  template <class S>
+  DDP_HD static void leg_trig(double sx, double sd, const S& sa, const S& ca, const S& sh, const S& ch, const S& sk,
+                              const S& ck, const S& va, const S& vh, const S& vk, const S& ua, const S& uh,
+                              const S& uk, const S& pz, const S* v, const BasePose<S>& B, const double* p,
+                              LegOut<S>& o) {
+    const double bj = p[9], l1 = p[10], l2 = p[11], l3 = p[12];
+    const double hx = p[13], hy = p[14], rf = p[15], E = p[16], mu = p[17], vs = p[18];
     const double ly = sd * l1;
     S lx = -(l2 * sh) - l3 * sk;
     S lz = -(l2 * ch) - l3 * ck;

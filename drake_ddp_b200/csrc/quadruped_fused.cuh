@@ -6,8 +6,9 @@
 // evaluations per point).  A leg's loads depend on 16 local inputs only (base height and
 // attitude, base twist, its own three joints and rates), so here
 //   1. per substep, the 4 x 16 (leg, local direction) pairs are dealt to the 32 lanes of a warp,
-//      two directions per lane, and Quadruped::leg is evaluated with Dual<2>: the same
-//      templates as the rollout, 64 dual leg evaluations per substep instead of 192;
+//      two directions per lane, and Quadruped::leg_trig is evaluated with Dual<2>: the same
+//      templates as the rollout, 64 dual leg evaluations per substep instead of 192; each of
+//      the 15 sines / cosines a substep needs is computed by one lane and shared by shuffle;
 //   2. every lane scatters its derivatives straight into the substep Jacobian in shared memory
 //      (base rows are summed over the legs with the same two-stage butterfly the rollout uses),
 //      the integrator rows follow element-wise (QuadJac::dq_elem);
@@ -26,7 +27,13 @@ namespace ddp {
 
 constexpr int kQfLd = 52;     // leading dimension of the Jacobians in shared memory (52 = 4 mod 16:
                               // conflict-free 8 x 4 and 4 x 8 DMMA operand fetches)
-constexpr int kQfWarps = 4;   // warps (points in flight) per CTA
+#ifndef QF_WARPS
+#define QF_WARPS 4
+#endif
+constexpr int kQfWarps = QF_WARPS;   // warps (points in flight) per CTA
+#ifndef QF_MINB
+#define QF_MINB 2
+#endif
 
 struct QfWarpSmem {
   double D1[36 * kQfLd];      // substep-1 Jacobian d(q1, v1)/d(q, v, u), 36 x 48
@@ -35,7 +42,7 @@ struct QfWarpSmem {
   double st[3][36];           // x_t, state after substep 1, after substep 2
 };
 
-__global__ void __launch_bounds__(kQfWarps * 32, 2)
+__global__ void __launch_bounds__(kQfWarps * 32, QF_MINB)
 quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   typedef Quadruped Qd;
   typedef Dual<2> D2;
@@ -67,14 +74,48 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   }
   __syncwarp();
 
-  for (int item = blockIdx.x * kQfWarps + warp; item < n_items; item += gridDim.x * kQfWarps) {
-    const int b = item / T, i = item % T;
-    if (!d.active[b] || i >= count[b]) continue;
-    const int t = list[(size_t)b * T + i];
+  // Points are taken grid-stride; the indices of the next point are fetched at the top of the
+  // current one and its state and controls after the first substep, so that the global-memory
+  // latency hides behind the arithmetic (8 warps per SM cannot hide it otherwise).
+  const int stride = gridDim.x * kQfWarps;
+  auto fetch_idx = [&](int it, int& bb, int& tt) -> bool {
+    if (it >= n_items) return false;
+    bb = it / T;
+    const int i = it % T;
+    if (!d.active[bb] || i >= count[bb]) return false;
+    tt = list[(size_t)bb * T + i];
+    return true;
+  };
+  struct Pt {
+    double x0, x1, ua, uh, uk;
+  };
+  auto fetch_pt = [&](int bb, int tt) {
+    Pt r;
+    const double* xp = d.x_bar + ((size_t)bb * d.N + tt) * 36;
+    const double* up = d.u_bar + ((size_t)bb * T + tt) * 12;
+    r.x0 = xp[lane];
+    r.x1 = (lane < 4) ? xp[32 + lane] : 0.0;
+    r.ua = up[3 * leg];
+    r.uh = up[3 * leg + 1];
+    r.uk = up[3 * leg + 2];
+    return r;
+  };
+  int item = blockIdx.x * kQfWarps + warp;
+  int b = 0, t = 0;
+  bool ok = fetch_idx(item, b, t);
+  Pt cur = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (ok) cur = fetch_pt(b, t);
+  while (item < n_items) {
+    int nb = 0, nt = 0;
+    const bool nok = fetch_idx(item + stride, nb, nt);
+    Pt nxt = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (!ok) {
+      if (nok) nxt = fetch_pt(nb, nt);
+    } else {
     const size_t bt = (size_t)b * T + t;
-    const double* up = d.u_bar + bt * 12;
-    for (int k = lane; k < 36; k += 32) s.st[0][k] = d.x_bar[((size_t)b * d.N + t) * 36 + k];
-    const double ua = up[3 * leg], uh = up[3 * leg + 1], uk = up[3 * leg + 2];
+    s.st[0][lane] = cur.x0;
+    if (lane < 4) s.st[0][32 + lane] = cur.x1;
+    const double ua = cur.ua, uh = cur.uh, uk = cur.uk;
     __syncwarp();
 
     double trig[2][4];   // sin/cos of roll and pitch at the start of each substep
@@ -91,21 +132,45 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         r.d[1] = (j == j1) ? 1.0 : 0.0;
         return r;
       };
-      D2 qb[6], vb[6];
-      qb[0] = D2(0.0); qb[1] = D2(0.0);
-      qb[2] = seed(xin[2], 0);
-      qb[3] = seed(xin[3], 1);
-      qb[4] = seed(xin[4], 2);
-      qb[5] = seed(xin[5], 3);
+      // one sincos per lane, shared by shuffle: lanes dp = 0..2 of a leg group take abad, hip,
+      // hip + knee of their leg, dp = 3..5 roll, pitch, yaw (same values in every group)
+      double sn, cs;
+      {
+        const double ang = (dp == 0)   ? xin[6 + 3 * leg]
+                           : (dp == 1) ? xin[7 + 3 * leg]
+                           : (dp == 2) ? (xin[7 + 3 * leg] + xin[8 + 3 * leg])
+                           : (dp == 3) ? xin[3]
+                           : (dp == 4) ? xin[4]
+                                       : xin[5];
+        sincos_(ang, &sn, &cs);
+      }
+      // dual sine / cosine of an angle whose value pair comes from lane `src` and whose seed
+      // weights along this lane's two directions are w0, w1
+      auto trig_dual = [&](int src, double w0, double w1, D2& sD, D2& cD) {
+        const double sv = __shfl_sync(full, sn, src), cv = __shfl_sync(full, cs, src);
+        sD.v = sv; sD.d[0] = cv * w0; sD.d[1] = cv * w1;
+        cD.v = cv; cD.d[0] = -sv * w0; cD.d[1] = -sv * w1;
+      };
+      auto w = [&](int j, int e) { return (j == (e ? j1 : j0)) ? 1.0 : 0.0; };
+      const int gl = lane & ~7;   // first lane of this leg's group
+      D2 vb[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) vb[k] = seed(xin[18 + k], 4 + k);
+      const D2 pz = seed(xin[2], 0);
       Qd::BasePose<D2> B;
-      Qd::base_pose(qb, B);
+      D2 sy, cy;
+      trig_dual(gl + 3, w(1, 0), w(1, 1), B.sr, B.cr);
+      trig_dual(gl + 4, w(2, 0), w(2, 1), B.sp, B.cp);
+      trig_dual(gl + 5, w(3, 0), w(3, 1), sy, cy);
+      Qd::base_pose_trig(sy, cy, B);
       trig[sub][0] = B.sr.v; trig[sub][1] = B.cr.v; trig[sub][2] = B.sp.v; trig[sub][3] = B.cp.v;
+      D2 sa, ca, sh, ch, sk, ck;
+      trig_dual(gl + 0, w(10, 0), w(10, 1), sa, ca);
+      trig_dual(gl + 1, w(11, 0), w(11, 1), sh, ch);
+      trig_dual(gl + 2, w(11, 0) + w(12, 0), w(11, 1) + w(12, 1), sk, ck);
       Qd::LegOut<D2> o;
-      Qd::leg(sx, sd, seed(xin[6 + 3 * leg], 10), seed(xin[7 + 3 * leg], 11), seed(xin[8 + 3 * leg], 12),
-              seed(xin[24 + 3 * leg], 13), seed(xin[25 + 3 * leg], 14), seed(xin[26 + 3 * leg], 15), D2(ua), D2(uh),
-              D2(uk), qb[2], vb, B, p, o);
+      Qd::leg_trig(sx, sd, sa, ca, sh, ch, sk, ck, seed(xin[24 + 3 * leg], 13), seed(xin[25 + 3 * leg], 14),
+                   seed(xin[26 + 3 * leg], 15), D2(ua), D2(uh), D2(uk), pz, vb, B, p, o);
       // ---- scatter: joint rows of this leg, base rows summed over the legs ---------------------
       {
         const D2* ja[3] = {&o.a0, &o.a1, &o.a2};
@@ -179,6 +244,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       }
       __syncwarp();
       if (sub == 0) {
+        if (nok) nxt = fetch_pt(nb, nt);   // next point's state and controls: consumed a substep later
         // position rows of D1 from its finished velocity rows (QuadJac::dq_elem)
         for (int r = 0; r < 18; ++r)
           for (int c = lane; c < 48; c += 32)
@@ -264,6 +330,12 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       }
     }
     __syncwarp();
+    }
+    ok = nok;
+    b = nb;
+    t = nt;
+    cur = nxt;
+    item += stride;
   }
 }
 
