@@ -15,6 +15,7 @@
 #include "backward_mma.cuh"
 #include "quadruped_linearize.cuh"
 #include "quadruped_fused.cuh"
+#include "quadruped_rollout.cuh"
 
 using namespace ddp;
 
@@ -41,6 +42,7 @@ struct ddp_solver {
   bool timings_valid;
   bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
   bool quad_structured;  // opt-in (DDP_QUAD_STRUCTURED=1): two-kernel structured quadruped linearization
+  bool quad_rollout8;    // 8-lane quadruped rollout (DDP_QUAD_ROLLOUT=generic selects rollout_kernel)
   bool quad_fused;       // fused structured quadruped linearization (DDP_QUAD_LINEARIZE=fused|ad)
   double* quadG;         // quadruped fast path: local leg Jacobians [B*T][sub][4][144]
   double* quadXmid;      //                      state after each substep [B*T][sub][36]
@@ -188,6 +190,12 @@ int launch_backward(ddp_solver* s) {
 }
 
 int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
+  if (s->model == MODEL_QUADRUPED && s->quad_rollout8) {
+    rollout_quad8_kernel<<<cdiv(n_items, kRqCands), kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base, per_traj,
+                                                                                         n_items);
+    s->launches++;
+    return 0;
+  }
   DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base, per_traj, n_items));
   return 0;
 }
@@ -442,6 +450,8 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   }
   s->quad_structured = getenv("DDP_QUAD_STRUCTURED") != nullptr;
   {
+    const char* rmode = getenv("DDP_QUAD_ROLLOUT");
+    s->quad_rollout8 = !(rmode && std::string(rmode) == "generic");
     // default: the fused structured kernel; DDP_QUAD_LINEARIZE=ad selects the generic AD kernel
     const char* mode = getenv("DDP_QUAD_LINEARIZE");
     s->quad_fused = !s->quad_structured && !(mode && std::string(mode) == "ad");
