@@ -341,12 +341,12 @@ def run_b200(args):
         dom = max(phase_ms, key=phase_ms.get)
         active_per_step = units_local / K
         if dom == "backward":
-            kernel, bytes_per_launch, launch_ms = "backward_kernel", pb["backward"] * active_per_step, phase_ms[dom] / K
+            kernel, bytes_per_launch, launch_ms = "backward_mma_kernel", pb["backward"] * active_per_step, phase_ms[dom] / K
         elif dom == "derivs":
-            kernel, bytes_per_launch, launch_ms = "linearize_kernel", pb["derivs"] * active_per_step, phase_ms[dom] / K
+            kernel, bytes_per_launch, launch_ms = "quad_fused_kernel", pb["derivs"] * active_per_step, phase_ms[dom] / K
         else:
             # line-search phase: every round launches one rollout kernel over A candidates
-            kernel = "rollout_kernel (line-search phase, all rounds)"
+            kernel = "rollout_quad8_kernel (line-search phase, all rounds)"
             bytes_per_launch = pb["rollout"] * active_per_step * float(np.mean(ls))
             launch_ms = phase_ms[dom] / K
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9

@@ -620,7 +620,7 @@ backward_mma_kernel(Dev d) {
       BWD_TICK(3);
       // Quu^-1 (ilqr.py:655): Newton-Schulz from the previous step's inverse; Wu is dead by
       // now, so its buffer is the scratch
-      if (t == T - 1 || !invert_newton_warp<m>(s.Quu, s.QuuInv, s.WuKt, s.WuKt + m * m)) {
+      if (t == T - 1 || (d.bwd_flags & 1) || !invert_newton_warp<m>(s.Quu, s.QuuInv, s.WuKt, s.WuKt + m * m)) {
         invert_warp<m>(s.Quu, s.QuuInv);
 #ifdef DDP_BWD_PROFILE
         if (lane == 0) atomicAdd(&g_bwd_fallbacks, 1);

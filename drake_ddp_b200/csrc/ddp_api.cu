@@ -450,6 +450,8 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   }
   s->quad_structured = getenv("DDP_QUAD_STRUCTURED") != nullptr;
   {
+    const char* inv = getenv("DDP_BWD_INVERSE");   // "gauss-jordan": no Newton-Schulz (debug / parity tests)
+    s->d.bwd_flags = (inv && std::string(inv) == "gauss-jordan") ? 1 : 0;
     const char* rmode = getenv("DDP_QUAD_ROLLOUT");
     s->quad_rollout8 = !(rmode && std::string(rmode) == "generic");
     // default: the fused structured kernel; DDP_QUAD_LINEARIZE=ad selects the generic AD kernel

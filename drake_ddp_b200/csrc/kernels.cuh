@@ -23,6 +23,7 @@ struct Dev {
   double *xc, *uc, *Lc, *Ec;
   double *L, *L_new, *eps, *improvement;
   int *ls_iters, *status, *active, *resolved, *acc, *iters, *counters, *unres;
+  int bwd_flags;  // bit 0: backward_mma_kernel inverts Quu by Gauss-Jordan at every step (no Newton-Schulz)
   int* sm_slots;  // per-SM bitmask of the CTA slots in use (backward_mma_kernel deals warp roles by slot)
   // keypoints
   int kp_method, minN, maxN;

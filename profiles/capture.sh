@@ -4,7 +4,7 @@
 TAG=${1:-r1}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
-for K in backward linearize rollout; do
+for K in backward quad_fused rollout; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o gpurun_out/prof_${K}_$TAG $CMD > gpurun_out/ncu_${K}_$TAG.log 2>&1
 done
 ls -la gpurun_out | tail -8

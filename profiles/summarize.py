@@ -27,7 +27,8 @@ METRICS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
     "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
 ]
 
 
@@ -83,7 +84,9 @@ def main():
           "`python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare shares).", ""]
     md += launches(tag) + [""]
     traffic = {}
-    for kern in ("backward", "linearize", "rollout"):
+    names = {"backward": "backward_mma_kernel", "quad_fused": "quad_fused_kernel", "rollout": "rollout_quad8_kernel",
+             "linearize": "linearize_kernel"}
+    for kern in ("backward", "quad_fused", "linearize", "rollout"):
         rep = os.path.join(GO, f"prof_{kern}_{tag}.ncu-rep")
         if not os.path.exists(rep):
             continue
@@ -99,8 +102,7 @@ def main():
             v, u = m[key]
             v = float(v.replace(",", ""))
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[u]
-        traffic[{"backward": "backward_kernel", "linearize": "linearize_kernel", "rollout": "rollout_kernel"}[kern]] = \
-            gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+        traffic[names[kern]] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
     open(os.path.join(OUT, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
     json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
     print("\n".join(md))

@@ -346,3 +346,53 @@ def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
                 fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
                 assert np.abs(out[mode][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max()), mode
                 assert np.abs(out[mode][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max()), mode
+
+
+def test_backward_newton_schulz_inverse_matches_gauss_jordan(monkeypatch):
+    """backward_mma_kernel inverts Quu by Newton-Schulz on the tensor pipe, seeded with the inverse
+    of the previous step, and falls back to Gauss-Jordan with partial pivoting when the seed does
+    not contract (csrc/backward_mma.cuh).  Both must give the gains of ilqr.py:655-660: compare the
+    default against DDP_BWD_INVERSE=gauss-jordan on the same linearization, smooth steps and
+    contact switches (half of the batch lands during the horizon) included."""
+    prob = problems.quadruped(80)
+    B = 8
+    rng = np.random.default_rng(11)
+    x0 = prob.batch_x0(B, seed=3)
+    x0[B // 2:, 2] += 0.03                        # dropped from 3 cm: touches down inside the horizon
+    out = {}
+    for mode in ("newton", "gauss-jordan"):
+        monkeypatch.delenv("DDP_BWD_INVERSE", raising=False)
+        if mode == "gauss-jordan":
+            monkeypatch.setenv("DDP_BWD_INVERSE", "gauss-jordan")
+        s = make_gpu(prob, B=B, x0=x0)
+        s.begin_solve()
+        s.iterate()
+        out[mode] = (s.get(_lib.K), s.get(_lib.KAPPA), s.get(_lib.DV), s.cost.copy())
+    for a, b_ in zip(out["newton"], out["gauss-jordan"]):
+        assert relerr(a, b_) < 1e-10
+
+
+def test_quadruped_rollout8_matches_generic_rollout(monkeypatch):
+    """The 8-lane quadruped rollout (csrc/quadruped_rollout.cuh) against the generic rollout kernel:
+    same candidates, same accepted step, states equal up to the association of the feedback sum."""
+    prob = problems.quadruped(60)
+    B = 6
+    x0 = prob.batch_x0(B, seed=2)
+    out = {}
+    for mode in ("quad8", "generic"):
+        monkeypatch.delenv("DDP_QUAD_ROLLOUT", raising=False)
+        if mode == "generic":
+            monkeypatch.setenv("DDP_QUAD_ROLLOUT", "generic")
+        s = make_gpu(prob, B=B, x0=x0, A=4)
+        s.begin_solve()
+        for _ in range(3):
+            s.iterate()
+        out[mode] = (s.get(_lib.X_BAR), s.get(_lib.U_BAR), s.cost.copy(), s.get_int(_lib.I_LS_ITERS).copy(),
+                     s.get(_lib.CAND_COST).copy())
+    assert np.array_equal(out["quad8"][3], out["generic"][3])
+    assert relerr(out["quad8"][0], out["generic"][0]) < 1e-10
+    assert relerr(out["quad8"][1], out["generic"][1]) < 1e-9
+    assert relerr(out["quad8"][2], out["generic"][2]) < 1e-11
+    fin = np.isfinite(out["generic"][4])
+    assert np.array_equal(fin, np.isfinite(out["quad8"][4]))
+    assert relerr(out["quad8"][4][fin], out["generic"][4][fin]) < 1e-10
