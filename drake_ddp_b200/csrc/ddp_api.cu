@@ -191,8 +191,11 @@ int launch_backward(ddp_solver* s) {
 
 int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
   if (s->model == MODEL_QUADRUPED && s->quad_rollout8) {
-    rollout_quad8_kernel<<<cdiv(n_items, kRqCands), kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base, per_traj,
-                                                                                         n_items);
+    if (ls_base == 0 && per_traj == kRqCands && n_items == s->d.B * kRqCands)
+      rollout_quad8_kernel<true><<<s->d.B, kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+    else
+      rollout_quad8_kernel<false><<<cdiv(n_items, kRqCands), kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base,
+                                                                                                  per_traj, n_items);
     s->launches++;
     return 0;
   }

@@ -32,16 +32,38 @@ struct RqCandSmem {
   double u[12];     // controls of the step
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+
+// SHARED: first line-search round with per_traj == kRqCands: the 8 candidates of a CTA belong to
+// one trajectory, so its per-step operands (K_t, x_bar_t, u_bar_t, kappa_t: 3936 bytes) are
+// staged once per CTA into a double buffer with cp.async, one step ahead, instead of being
+// fetched by every candidate through L1.
+constexpr int kRqStage = 432 + 36 + 12 + 12;   // doubles per staged step
+
+template <bool SHARED>
 __global__ void __launch_bounds__(kRqLanes * kRqCands, 7)
 rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   typedef Quadruped Qd;
   constexpr int n = 36, m = 12;
   __shared__ RqCandSmem sm[kRqCands];
+  __shared__ __align__(16) double stage_buf[SHARED ? 2 : 1][SHARED ? kRqStage : 2];
   const int cand = threadIdx.x >> 3, lane = threadIdx.x & 7;
   const int item = blockIdx.x * kRqCands + cand;
-  if (item >= n_items) return;
+  bool alive = true;   // SHARED: a finished candidate keeps taking part in the CTA barriers
+  if (item >= n_items) {
+    if (!SHARED) return;
+    alive = false;
+  }
   int b, ai;
-  if (ls_base == 0) {
+  if (SHARED) {        // launcher guarantees ls_base == 0, per_traj == kRqCands
+    b = blockIdx.x;
+    ai = cand;
+    if (!d.active[b] || d.resolved[b]) return;   // uniform over the CTA
+  } else if (ls_base == 0) {
     b = item / per_traj;
     ai = item % per_traj;
     if (!d.active[b] || d.resolved[b]) return;
@@ -50,12 +72,13 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
     ai = item % per_traj;
   }
   const int c = ls_base + ai;
-  if (c >= d.n_eps) {
+  if (alive && c >= d.n_eps) {
     if (lane == 0) {
       d.Lc[item] = nan("");
       d.Ec[item] = 0.0;
     }
-    return;
+    if (!SHARED) return;
+    alive = false;
   }
   const int wl = threadIdx.x & 31, gbase = wl & ~7;
   const unsigned mask = 0xFFu << gbase;
@@ -63,7 +86,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   const double* p = d.params;
   const int sub_n = (int)p[1];
   const double h = p[0] / sub_n;
-  const double eps = d.eps_table[c];
+  const double eps = d.eps_table[min(c, d.n_eps - 1)];
   const double ecoef = -eps * (1.0 - eps / 2.0);
   const int N = d.N, T = d.T;
   const double* xnom = d.x_nom + (size_t)b * n;
@@ -80,19 +103,36 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   for (int j = lane; j < n; j += kRqLanes) {
     const double v = d.x0[(size_t)b * n + j];
     s.x[j] = v;
-    xo[j] = v;
+    if (alive) xo[j] = v;
   }
   __syncwarp(mask);
+  auto stage = [&](int t, int buf) {   // SHARED: all threads of the CTA
+    char* dst = reinterpret_cast<char*>(stage_buf[buf]);
+    const char* gK = reinterpret_cast<const char*>(d.K + ((size_t)b * d.T + t) * m * n);
+    for (int ch = threadIdx.x; ch < 216; ch += kRqLanes * kRqCands) cp_async16(dst + 16 * ch, gK + 16 * ch);
+    const int q = threadIdx.x;
+    if (q < 18) cp_async16(dst + 3456 + 16 * q, reinterpret_cast<const char*>(d.x_bar + ((size_t)b * d.N + t) * n) + 16 * q);
+    else if (q < 24) cp_async16(dst + 3744 + 16 * (q - 18), reinterpret_cast<const char*>(d.u_bar + ((size_t)b * d.T + t) * m) + 16 * (q - 18));
+    else if (q < 30) cp_async16(dst + 3840 + 16 * (q - 24), reinterpret_cast<const char*>(d.kappa + ((size_t)b * d.T + t) * m) + 16 * (q - 24));
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (SHARED) stage(0, 0);
 
   // cost weights of this lane's entries (diagonal costs)
   double L = 0.0, E = 0.0;
   bool ok = true;
   for (int t = 0; t < T; ++t) {
-    const double* Kt = d.K + ((size_t)b * T + t) * m * n;
-    const double* xb = d.x_bar + ((size_t)b * N + t) * n;
-    const double* ub = d.u_bar + ((size_t)b * T + t) * m;
-    const double* kp = d.kappa + ((size_t)b * T + t) * m;
-    if (t + 1 < T) {   // pull the next step's gain half-rows towards L1 while this step computes
+    if (SHARED) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();   // step t staged and visible; everybody is done with the other buffer
+      if (t + 1 < T) stage(t + 1, (t + 1) & 1);
+      if (!alive) continue;
+    }
+    const double* Kt = SHARED ? stage_buf[t & 1] : d.K + ((size_t)b * T + t) * m * n;
+    const double* xb = SHARED ? stage_buf[t & 1] + 432 : d.x_bar + ((size_t)b * N + t) * n;
+    const double* ub = SHARED ? stage_buf[t & 1] + 468 : d.u_bar + ((size_t)b * T + t) * m;
+    const double* kp = SHARED ? stage_buf[t & 1] + 480 : d.kappa + ((size_t)b * T + t) * m;
+    if (!SHARED && t + 1 < T) {   // pull the next step's gain half-rows towards L1 while this step computes
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const char* pr = reinterpret_cast<const char*>(Kt + (size_t)m * n + (size_t)(prow + 4 * i) * n + 18 * hh);
@@ -223,7 +263,9 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
     for (int j = lane; j < n; j += kRqLanes) fin = fin && isfinite(s.x[j]);
     if (!__all_sync(mask, fin)) {  // the reference gets a RuntimeError from Drake: L = inf, stop (:317-323)
       ok = false;
-      break;
+      if (!SHARED) break;
+      alive = false;   // keep taking part in the CTA barriers
+      continue;
     }
     E += ecoef * d.dV[(size_t)b * T + t];                      //  (ilqr.py:326)
     for (int j = lane; j < n; j += kRqLanes) xo[(size_t)(t + 1) * n + j] = s.x[j];
@@ -250,7 +292,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   } else {
     L = INFINITY;
   }
-  if (lane == 0) {
+  if (lane == 0 && (alive || !ok)) {
     d.Lc[item] = L;
     d.Ec[item] = E;
   }
