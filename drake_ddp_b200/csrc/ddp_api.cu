@@ -742,6 +742,13 @@ int ddp_peak_fp64(void* stream, int use_mma, double* tflops) {
   return 0;
 }
 
+#ifdef DDP_ROLL_PROFILE
+int ddp_debug_roll_profile(long long* out16) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out16, ddp::g_roll_prof, sizeof(long long) * 16));
+  return 0;
+}
+#endif
 #ifdef DDP_BWD_PROFILE
 // debug builds only: per-phase cycle totals recorded by backward_mma_kernel
 int ddp_debug_bwd_profile(long long* out64) {

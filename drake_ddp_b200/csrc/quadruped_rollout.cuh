@@ -40,9 +40,23 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 
 // SHARED: first line-search round with per_traj == kRqCands: the 8 candidates of a CTA belong to
 // one trajectory, so its per-step operands (K_t, x_bar_t, u_bar_t, kappa_t: 3936 bytes) are
-// staged once per CTA into a double buffer with cp.async, one step ahead, instead of being
-// fetched by every candidate through L1.
+// staged once per warp (4 candidates) into a double buffer with cp.async, one step ahead,
+// instead of being fetched by every candidate through L1.
 constexpr int kRqStage = 432 + 36 + 12 + 12;   // doubles per staged step
+
+#ifdef DDP_ROLL_PROFILE
+__device__ long long g_roll_prof[16];
+#define ROLL_TICK(i)                                 \
+  do {                                               \
+    if (rprof) {                                     \
+      const long long now_ = clock64();              \
+      racc[i] += now_ - rlast;                       \
+      rlast = now_;                                  \
+    }                                                \
+  } while (0)
+#else
+#define ROLL_TICK(i)
+#endif
 
 template <bool SHARED>
 __global__ void __launch_bounds__(kRqLanes * kRqCands, 7)
@@ -50,7 +64,10 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   typedef Quadruped Qd;
   constexpr int n = 36, m = 12;
   __shared__ RqCandSmem sm[kRqCands];
-  __shared__ __align__(16) double stage_buf[SHARED ? 2 : 1][SHARED ? kRqStage : 2];
+  // [warp][buffer][operands of one step]: every warp (4 candidates) keeps its own copy, so only
+  // warp-level synchronisation is needed
+  __shared__ __align__(16) double stage_all[SHARED ? 2 : 1][SHARED ? 2 : 1][SHARED ? kRqStage : 2];
+  double (*stage_buf)[SHARED ? kRqStage : 2] = stage_all[SHARED ? (threadIdx.x >> 5) : 0];
   const int cand = threadIdx.x >> 3, lane = threadIdx.x & 7;
   const int item = blockIdx.x * kRqCands + cand;
   bool alive = true;   // SHARED: a finished candidate keeps taking part in the CTA barriers
@@ -106,11 +123,11 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
     if (alive) xo[j] = v;
   }
   __syncwarp(mask);
-  auto stage = [&](int t, int buf) {   // SHARED: all threads of the CTA
+  auto stage = [&](int t, int buf) {   // SHARED: all threads of the warp
     char* dst = reinterpret_cast<char*>(stage_buf[buf]);
     const char* gK = reinterpret_cast<const char*>(d.K + ((size_t)b * d.T + t) * m * n);
-    for (int ch = threadIdx.x; ch < 216; ch += kRqLanes * kRqCands) cp_async16(dst + 16 * ch, gK + 16 * ch);
-    const int q = threadIdx.x;
+    for (int ch = wl; ch < 216; ch += 32) cp_async16(dst + 16 * ch, gK + 16 * ch);
+    const int q = wl;
     if (q < 18) cp_async16(dst + 3456 + 16 * q, reinterpret_cast<const char*>(d.x_bar + ((size_t)b * d.N + t) * n) + 16 * q);
     else if (q < 24) cp_async16(dst + 3744 + 16 * (q - 18), reinterpret_cast<const char*>(d.u_bar + ((size_t)b * d.T + t) * m) + 16 * (q - 18));
     else if (q < 30) cp_async16(dst + 3840 + 16 * (q - 24), reinterpret_cast<const char*>(d.kappa + ((size_t)b * d.T + t) * m) + 16 * (q - 24));
@@ -118,20 +135,41 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   };
   if (SHARED) stage(0, 0);
 
-  // cost weights of this lane's entries (diagonal costs)
+  // diagonal cost: weights and targets of this lane's entries (states lane + 8k, controls lane + 8k)
+  double wq[5], wf[5], xn_[5], wr[2];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int j = lane + kRqLanes * k;
+    wq[k] = (j < n) ? d.Q[j * n + j] : 0.0;
+    wf[k] = (j < n) ? d.Qf[j * n + j] : 0.0;
+    xn_[k] = (j < n) ? xnom[j] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + kRqLanes * k;
+    wr[k] = (r < m) ? d.R[r * m + r] : 0.0;
+  }
   double L = 0.0, E = 0.0;
   bool ok = true;
+#ifdef DDP_ROLL_PROFILE
+  const bool rprof = SHARED && (blockIdx.x == 3 && threadIdx.x == 0);
+  long long racc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long rlast = clock64();
+#endif
   for (int t = 0; t < T; ++t) {
+    ROLL_TICK(0);
     if (SHARED) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();   // step t staged and visible; everybody is done with the other buffer
+      __syncwarp();      // step t staged and visible; the whole warp is done with the other buffer
       if (t + 1 < T) stage(t + 1, (t + 1) & 1);
       if (!alive) continue;
     }
+    ROLL_TICK(1);
     const double* Kt = SHARED ? stage_buf[t & 1] : d.K + ((size_t)b * T + t) * m * n;
     const double* xb = SHARED ? stage_buf[t & 1] + 432 : d.x_bar + ((size_t)b * N + t) * n;
     const double* ub = SHARED ? stage_buf[t & 1] + 468 : d.u_bar + ((size_t)b * T + t) * m;
     const double* kp = SHARED ? stage_buf[t & 1] + 480 : d.kappa + ((size_t)b * T + t) * m;
+    const double dv_t = d.dV[(size_t)b * T + t];   // issued early, consumed at the end of the step
     if (!SHARED && t + 1 < T) {   // pull the next step's gain half-rows towards L1 while this step computes
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -167,15 +205,25 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       }
     }
     __syncwarp(mask);
+    ROLL_TICK(2);
     // ---- running cost uses the pre-step state                         (ilqr.py:325) ----------
     {
       double sacc = 0.0;
       if (diag) {
-        for (int j = lane; j < n; j += kRqLanes) {
-          const double e = s.x[j] - xnom[j];
-          sacc = fma(d.Q[j * n + j] * e, e, sacc);
+        double pt[7];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int j = lane + kRqLanes * k;
+          const double e = ((j < n) ? s.x[j] : 0.0) - xn_[k];
+          pt[k] = (wq[k] * e) * e;
         }
-        for (int r = lane; r < m; r += kRqLanes) sacc = fma(d.R[r * m + r] * s.u[r], s.u[r], sacc);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int r = lane + kRqLanes * k;
+          const double uu = (r < m) ? s.u[r] : 0.0;
+          pt[5 + k] = (wr[k] * uu) * uu;
+        }
+        sacc = ((pt[0] + pt[1]) + (pt[2] + pt[3])) + ((pt[4] + pt[5]) + pt[6]);
       } else {
         for (int j = lane; j < n; j += kRqLanes) {
           double row = 0.0;
@@ -191,8 +239,10 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       L += sacc;
       for (int r = lane; r < m; r += kRqLanes) uo[(size_t)t * m + r] = s.u[r];
     }
+    ROLL_TICK(3);
     const double ua = s.u[3 * leg], uh = s.u[3 * leg + 1], uk = s.u[3 * leg + 2];
     // ---- x_{t+1} = f(x_t, u_t)                                          (ilqr.py:316) ----------
+    bool fin_step = true;
     for (int it = 0; it < sub_n; ++it) {
       // two sincos per lane: even lane of leg l: abad, hip + knee; odd lane: hip, one base angle
       const double qh_ = s.x[7 + 3 * leg];
@@ -201,6 +251,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       double s1, c1, s2, c2;
       sincos_(ang1, &s1, &c1);
       sincos_(ang2, &s2, &c2);
+      ROLL_TICK(4);
       Qd::BasePose<double> B;
       B.sr = __shfl_sync(mask, s2, gbase + 1);
       B.cr = __shfl_sync(mask, c2, gbase + 1);
@@ -222,61 +273,90 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
         s.acc[7 + 3 * leg] = o.a1;
         s.acc[8 + 3 * leg] = o.a2;
       }
+      ROLL_TICK(5);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         f[k] += __shfl_xor_sync(mask, f[k], 1);   // odd lanes hold 0
         f[k] += __shfl_xor_sync(mask, f[k], 2);
         f[k] += __shfl_xor_sync(mask, f[k], 4);
       }
-      if (lane == 0) {
-        double accb[18];
-        Qd::base_acc(f[0], f[1], f[2], f[3], f[4], f[5], vb, p, accb);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s.acc[k] = accb[k];
-      }
-      __syncwarp(mask);
-      // semi-implicit Euler (Quadruped::integrate): v+ first, then q+ = q + h N(q) v+
-      for (int i = lane; i < 18; i += kRqLanes) s.vn[i] = s.x[18 + i] + h * s.acc[i];
-      __syncwarp(mask);
+      ROLL_TICK(6);
+      // base accelerations (Quadruped::base_acc): entry k on lane k, one division per lane
+      // (numerator and denominator are selected branch-free)
       {
-        const double tp = B.sp / B.cp;
-        const double wyz = B.sr * s.vn[4] + B.cr * s.vn[5];
-        double qn[3];
-        int cnt = 0;
-        for (int i = lane; i < 18; i += kRqLanes, ++cnt) {
-          double rate = s.vn[i];
-          if (i == 3) rate = s.vn[3] + tp * wyz;
-          if (i == 4) rate = B.cr * s.vn[4] - B.sr * s.vn[5];
-          if (i == 5) rate = wyz / B.cp;
-          qn[cnt] = s.x[i] + h * rate;
+        const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5], grav = p[19];
+        const double n3 = f[3] - (Iz - Iy) * vb[4] * vb[5];
+        const double n4 = f[4] - (Ix - Iz) * vb[5] * vb[3];
+        const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
+        const double num = (lane == 0) ? f[0] : (lane == 1) ? f[1] : (lane == 2) ? f[2] : (lane == 3) ? n3 : (lane == 4) ? n4 : n5;
+        const double den = (lane < 3) ? mass : (lane == 3) ? Ix : (lane == 4) ? Iy : Iz;
+        double a = num / den;
+        if (lane == 2) a -= grav;
+        if (lane < 6) s.acc[lane] = a;
+      }
+      const double tp = B.sp / B.cp;
+      __syncwarp(mask);
+      ROLL_TICK(7);
+      // semi-implicit Euler (Quadruped::integrate): v+ first, then q+ = q + h N(q) v+; entries
+      // lane, lane + 8, lane + 16; the Euler-rate rows 3..5 get v+ of 3..5 by shuffle
+      {
+        double vn[3], qn[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = lane + kRqLanes * k;
+          vn[k] = (i < 18) ? (s.x[18 + i] + h * s.acc[i]) : 0.0;
+        }
+        const double w3 = __shfl_sync(mask, vn[0], gbase + 3), w4 = __shfl_sync(mask, vn[0], gbase + 4),
+                     w5 = __shfl_sync(mask, vn[0], gbase + 5);
+        const double wyz = B.sr * w4 + B.cr * w5;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = lane + kRqLanes * k;
+          double rate = vn[k];
+          if (k == 0) {
+            if (lane == 3) rate = w3 + tp * wyz;
+            if (lane == 4) rate = B.cr * w4 - B.sr * w5;
+            if (lane == 5) rate = wyz / B.cp;
+          }
+          qn[k] = (i < 18) ? (s.x[i] + h * rate) : 0.0;
+          fin_step = fin_step && isfinite(qn[k]) && isfinite(vn[k]);
         }
         __syncwarp(mask);   // every read of the old state done
-        cnt = 0;
-        for (int i = lane; i < 18; i += kRqLanes, ++cnt) {
-          s.x[i] = qn[cnt];
-          s.x[18 + i] = s.vn[i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = lane + kRqLanes * k;
+          if (i < 18) {
+            s.x[i] = qn[k];
+            s.x[18 + i] = vn[k];
+          }
         }
       }
       __syncwarp(mask);
+      ROLL_TICK(8);
     }
-    bool fin = true;
-    for (int j = lane; j < n; j += kRqLanes) fin = fin && isfinite(s.x[j]);
-    if (!__all_sync(mask, fin)) {  // the reference gets a RuntimeError from Drake: L = inf, stop (:317-323)
+    if (!__all_sync(mask, fin_step)) {  // the reference gets a RuntimeError from Drake: L = inf, stop (:317-323)
       ok = false;
       if (!SHARED) break;
-      alive = false;   // keep taking part in the CTA barriers
+      alive = false;   // keep taking part in the warp barriers
       continue;
     }
-    E += ecoef * d.dV[(size_t)b * T + t];                      //  (ilqr.py:326)
+    E += ecoef * dv_t;                      //  (ilqr.py:326)
     for (int j = lane; j < n; j += kRqLanes) xo[(size_t)(t + 1) * n + j] = s.x[j];
+    ROLL_TICK(9);
   }
+#ifdef DDP_ROLL_PROFILE
+  if (rprof)
+    for (int i = 0; i < 12; ++i) g_roll_prof[i] = racc[i];
+#endif
   // terminal cost                                                   (ilqr.py:327)
   if (ok) {
     double sacc = 0.0;
     if (diag) {
-      for (int j = lane; j < n; j += kRqLanes) {
-        const double e = s.x[j] - xnom[j];
-        sacc = fma(d.Qf[j * n + j] * e, e, sacc);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int j = lane + kRqLanes * k;
+        const double e = ((j < n) ? s.x[j] : 0.0) - xn_[k];
+        sacc = fma(wf[k] * e, e, sacc);
       }
     } else {
       for (int j = lane; j < n; j += kRqLanes) {

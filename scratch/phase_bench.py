@@ -69,3 +69,11 @@ if os.environ.get("PB_PROF"):
             tot = a[cta, w].sum()
             print("cta", cta, "dmma-warp" if w == 0 else "vector   ", "cycles/step", int(tot / (N - 1)),
                   {nm: int(v / (N - 1)) for nm, v in zip(names, a[cta, w])})
+
+if os.environ.get("PB_ROLLPROF"):
+    import ctypes
+    buf = (ctypes.c_longlong * 16)()
+    _lib.lib().ddp_debug_roll_profile(buf)
+    names = ["loop", "stage-wait", "feedback", "cost", "sincos", "leg", "butterfly", "base_acc", "integrate", "tail"]
+    tot = sum(buf[:10])
+    print("rollout cycles/step", int(tot / (N - 1)), {nm: int(v / (N - 1)) for nm, v in zip(names, buf[:10])})
