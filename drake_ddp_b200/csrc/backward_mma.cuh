@@ -220,6 +220,11 @@ __device__ __forceinline__ void st_pair(double* P, int idx, bool ok0, bool ok1, 
   }
 }
 
+#ifdef DDP_BWD_PROFILE
+__device__ int g_bwd_fallbacks;  // Gauss-Jordan inversions (first step of every trajectory included)
+__device__ int g_bwd_passes;     // Newton-Schulz passes, all inversions
+#endif
+
 // Inverse of the m x m matrix A by Newton-Schulz iteration on the fp64 tensor pipe, one warp:
 //   R = I - A X ;  X <- X + X R      (error squares every pass)
 // started from the inverse of the previous backward step, which is still in X: Quu moves little
@@ -313,6 +318,9 @@ __device__ __forceinline__ bool invert_newton_warp(const double* A, double* X, d
         if (r < m && c + 1 < m) Xs[r * m + c + 1] = xc[mt][nt][1];
       }
     __syncwarp();
+#ifdef DDP_BWD_PROFILE
+    if (lane == 0) atomicAdd(&g_bwd_passes, 1);
+#endif
     if (hmax < 0x3E700000u) {  // max |R| < 2^-24 before this pass: error now below an ulp
       ok = true;
       break;
@@ -334,7 +342,7 @@ static_assert(sizeof(BwdMmaSmem<36, 12>) <= 57088, "backward_mma_kernel: shared 
 #ifdef DDP_BWD_PROFILE
 // per-phase cycle totals of one DMMA warp and the vector warp of two CTAs (first / second wave)
 __device__ long long g_bwd_prof[2][2][16];
-__device__ int g_bwd_fallbacks;  // Gauss-Jordan inversions (first step of every trajectory included)
+
 #define BWD_TICK(i)                                                     \
   do {                                                                  \
     if (prof_on) {                                                      \

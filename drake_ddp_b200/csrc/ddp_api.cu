@@ -758,6 +758,10 @@ int ddp_debug_bwd_profile(long long* out64) {
   CK(cudaMemcpyFromSymbol(&fb, ddp::g_bwd_fallbacks, sizeof(int)));
   CK(cudaMemcpyToSymbol(ddp::g_bwd_fallbacks, &zero, sizeof(int)));
   out64[63] = fb;
+  int ps = 0;
+  CK(cudaMemcpyFromSymbol(&ps, ddp::g_bwd_passes, sizeof(int)));
+  CK(cudaMemcpyToSymbol(ddp::g_bwd_passes, &zero, sizeof(int)));
+  out64[62] = ps;
   return 0;
 }
 #endif

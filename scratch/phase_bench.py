@@ -61,7 +61,7 @@ if os.environ.get("PB_PROF"):
     import ctypes
     buf = (ctypes.c_longlong * 64)()
     _lib.lib().ddp_debug_bwd_profile(buf)
-    print('gauss-jordan fallbacks (all launches):', buf[63], 'of', B * (N - 1), 'per launch')
+    print('gauss-jordan fallbacks (all launches):', buf[63], 'of', B * (N - 1), 'per launch; newton passes (all launches):', buf[62])
     a = np.array(buf[:], dtype=np.int64).reshape(2, 2, 16)[:, :, :11]
     names = ["loop", "mbar", "A1+bar|lxlu", "A2|waitQuu", "A3+bar|inv", "B", "S1", "C1", "bar1", "C2|vecC", "S2"]
     for cta in range(2):
