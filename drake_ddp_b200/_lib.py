@@ -26,7 +26,8 @@ SYMBOLS = [
     "ddp_last_error", "ddp_model_dims", "ddp_workspace_bytes", "ddp_create", "ddp_destroy",
     "ddp_set_options", "ddp_set_keypoints", "ddp_set_cost", "ddp_set_target",
     "ddp_set_initial_state", "ddp_set_initial_guess", "ddp_reset", "ddp_begin_solve",
-    "ddp_iterate", "ddp_solve", "ddp_run_phase", "ddp_get",
+    "ddp_iterate", "ddp_iterate_linesearch", "ddp_iterate_finish_async", "ddp_iterate_wait", "ddp_solve",
+    "ddp_run_phase", "ddp_get",
     "ddp_put", "ddp_get_int", "ddp_device_ptr", "ddp_array_elems", "ddp_last_timings",
     "ddp_launch_count", "ddp_peak_fp64", "ddp_mpc_shift",
 ]
@@ -91,6 +92,9 @@ def lib():
     L.ddp_begin_solve.argtypes = [c_vp]
     L.ddp_mpc_shift.argtypes = [c_vp, c_int]
     L.ddp_iterate.argtypes = [c_vp, ip]
+    L.ddp_iterate_linesearch.argtypes = [c_vp]
+    L.ddp_iterate_finish_async.argtypes = [c_vp]
+    L.ddp_iterate_wait.argtypes = [c_vp, ip]
     L.ddp_solve.argtypes = [c_vp, c_int, ip]
     L.ddp_run_phase.argtypes = [c_vp, c_int]
     L.ddp_get.argtypes = [c_vp, c_int, c_vp]

@@ -328,14 +328,18 @@ int phase_derivatives(ddp_solver* s) {
   return 0;
 }
 
-int iterate_impl(ddp_solver* s, bool sync, bool force_all) {
+int iterate_linesearch_impl(ddp_solver* s, bool sync, bool force_all) {
   Dev& d = s->d;
   LAUNCH1(begin_iter_kernel, d, force_all ? 1 : 0);
   CK(cudaEventRecord(s->ev[0], s->stream));
   int rc = phase_linesearch(s, sync);
   if (rc) return rc;
   CK(cudaEventRecord(s->ev[1], s->stream));
-  rc = phase_derivatives(s);
+  return 0;
+}
+int iterate_finish_impl(ddp_solver* s) {
+  Dev& d = s->d;
+  int rc = phase_derivatives(s);
   if (rc) return rc;
   CK(cudaEventRecord(s->ev[2], s->stream));
   rc = do_backward(s);
@@ -345,6 +349,11 @@ int iterate_impl(ddp_solver* s, bool sync, bool force_all) {
   s->timings_valid = true;
   CK(cudaGetLastError());
   return 0;
+}
+int iterate_impl(ddp_solver* s, bool sync, bool force_all) {
+  int rc = iterate_linesearch_impl(s, sync, force_all);
+  if (rc) return rc;
+  return iterate_finish_impl(s);
 }
 
 struct ArrInfo {
@@ -625,6 +634,29 @@ int ddp_iterate(ddp_solver_t* s, int* n_active) {
   if (rc) return rc;
   CK(cudaMemcpyAsync(s->h_counters + 1, s->d.counters + 1, sizeof(int), cudaMemcpyDeviceToHost,
                      s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  if (n_active) *n_active = s->h_counters[1];
+  return 0;
+}
+
+int ddp_iterate_linesearch(ddp_solver_t* s) {
+  int rc = iterate_linesearch_impl(s, true, false);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int ddp_iterate_finish_async(ddp_solver_t* s) {
+  int rc = iterate_finish_impl(s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(s->h_counters + 1, s->d.counters + 1, sizeof(int), cudaMemcpyDeviceToHost,
+                     s->stream));
+  return 0;
+}
+
+int ddp_iterate_wait(ddp_solver_t* s, int* n_active) {
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
   if (n_active) *n_active = s->h_counters[1];

@@ -158,6 +158,23 @@ class BatchedILQR:
         _lib.check(self._L.ddp_iterate(self._h, ctypes.byref(n_active)), "ddp_iterate")
         return n_active.value
 
+    # one iteration in three calls (include/ddp_b200.h): the line search is synchronous, the
+    # derivatives + backward pass are enqueued and waited for separately, so the caller can move
+    # host buffers while they run (HostExchange below)
+    def iterate_linesearch(self):
+        _lib.check(self._L.ddp_iterate_linesearch(self._h), "ddp_iterate_linesearch")
+
+    def iterate_finish_async(self):
+        _lib.check(self._L.ddp_iterate_finish_async(self._h), "ddp_iterate_finish_async")
+
+    def iterate_wait(self) -> int:
+        n_active = ctypes.c_int()
+        _lib.check(self._L.ddp_iterate_wait(self._h, ctypes.byref(n_active)), "ddp_iterate_wait")
+        return n_active.value
+
+    def host_exchange(self):
+        return HostExchange(self)
+
     def solve(self, max_iters=0) -> int:
         it = ctypes.c_int()
         _lib.check(self._L.ddp_solve(self._h, int(max_iters), ctypes.byref(it)), "ddp_solve")
@@ -226,6 +243,71 @@ class BatchedILQR:
     @property
     def status(self):
         return self.get_int(_lib.I_STATUS)
+
+
+class HostExchange:
+    """Host <-> device traffic of an MPC-style loop overlapped with the iteration.
+
+    Every iteration of such a loop (acrobot.py:142-160, mini_cheetah.py:186-206) sends x0 and a
+    control tape to the solver and reads the new tape back.  The tape of an iteration is final
+    after its line search, and the derivatives + backward pass that follow only read it, so
+
+        ex.stage_inputs(x0_pinned, u_pinned)      # H2D into a staging buffer, copy stream
+        loop:
+            ex.apply_inputs()                     # staging -> x0, u_bar (device copy, solver stream)
+            solver.iterate_linesearch()
+            ex.read_controls(u_pinned)            # D2H of u_bar on the copy stream ...
+            solver.iterate_finish_async()         # ... under derivatives + backward pass
+            ex.wait_controls()                    # the host owns the new tape
+            ex.stage_inputs(x0_pinned, u_pinned)  # next inputs travel under the backward pass
+            solver.iterate_wait()
+
+    moves the same bytes as set_initial_* / get per iteration but hides them behind the kernels.
+    The staging buffer decouples the upload from u_bar, which the backward pass is still reading.
+    """
+
+    def __init__(self, solver: "BatchedILQR"):
+        torch = solver._torch
+        self.s = solver
+        self._torch = torch
+        dev = solver.device
+        self.copy_in = torch.cuda.Stream(device=dev)
+        self.copy_out = torch.cuda.Stream(device=dev)
+        self.stage_x0 = torch.empty((solver.B, solver.n), dtype=torch.float64, device=dev)
+        self.stage_u = torch.empty((solver.B, solver.T, solver.m), dtype=torch.float64, device=dev)
+        self.ev_staged = torch.cuda.Event()
+        self.ev_applied = torch.cuda.Event()
+        self.ev_read = torch.cuda.Event()
+        self._x0 = solver.device_tensor(_lib.X0)
+        self._u = solver.device_tensor(_lib.U_BAR)
+        self.ev_applied.record(solver._stream)
+
+    def stage_inputs(self, x0_pinned, u_pinned):
+        torch = self._torch
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(self.ev_applied)   # the previous staging content has been consumed
+            self.stage_x0.copy_(x0_pinned, non_blocking=True)
+            self.stage_u.copy_(u_pinned, non_blocking=True)
+            self.ev_staged.record(self.copy_in)
+
+    def apply_inputs(self):
+        torch = self._torch
+        st = self.s._stream
+        with torch.cuda.stream(st):
+            st.wait_event(self.ev_staged)
+            self._x0.copy_(self.stage_x0, non_blocking=True)
+            self._u.copy_(self.stage_u, non_blocking=True)
+            self.ev_applied.record(st)
+
+    def read_controls(self, u_pinned):
+        """Call after iterate_linesearch() (u_bar final, solver stream idle)."""
+        torch = self._torch
+        with torch.cuda.stream(self.copy_out):
+            u_pinned.copy_(self._u, non_blocking=True)
+            self.ev_read.record(self.copy_out)
+
+    def wait_controls(self):
+        self.ev_read.synchronize()
 
 
 class IterativeLinearQuadraticRegulator:

@@ -137,6 +137,21 @@ int ddp_begin_solve(ddp_solver_t* s);
 int ddp_iterate(ddp_solver_t* s, int* n_active);
 int ddp_solve(ddp_solver_t* s, int max_iters, int* iters_done);
 
+/* ddp_iterate in three calls, for callers that exchange host buffers every iteration (MPC
+ * loops, acrobot.py:142-160 / mini_cheetah.py:186-206):
+ *   ddp_iterate_linesearch    _linesearch + commit (ilqr.py:274-337, 375-376); returns when u_bar,
+ *                             x_bar of the iteration are final (the line search is synchronous:
+ *                             its rounds are sized from the number of unresolved trajectories);
+ *   ddp_iterate_finish_async  enqueues _get_derivatives + _backward_pass (ilqr.py:380-415,
+ *                             623-667) and the bookkeeping of :706-708 on the solver's stream and
+ *                             returns; they only read u_bar / x_bar, so the caller may copy the
+ *                             new controls to the host on another stream meanwhile;
+ *   ddp_iterate_wait          waits for them and returns how many trajectories remain active.
+ * ddp_iterate(s, n) == linesearch; finish_async; wait(n). */
+int ddp_iterate_linesearch(ddp_solver_t* s);
+int ddp_iterate_finish_async(ddp_solver_t* s);
+int ddp_iterate_wait(ddp_solver_t* s, int* n_active);
+
 /* One phase only (teacher-forced tests). */
 int ddp_run_phase(ddp_solver_t* s, int phase);
 

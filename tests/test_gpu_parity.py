@@ -396,3 +396,36 @@ def test_quadruped_rollout8_matches_generic_rollout(monkeypatch):
     fin = np.isfinite(out["generic"][4])
     assert np.array_equal(fin, np.isfinite(out["quad8"][4]))
     assert relerr(out["quad8"][4][fin], out["generic"][4][fin]) < 1e-10
+
+
+def test_split_iterate_and_host_exchange_equal_iterate():
+    """ddp_iterate_linesearch / _finish_async / _wait with the overlapped host exchange
+    (HostExchange: staged upload, control read-back under the backward pass) give bit-identical
+    results to ddp_iterate with blocking set_initial_* / get."""
+    import torch
+    prob = problems.quadruped(40)
+    B = 5
+    x0 = prob.batch_x0(B, seed=4)
+    u0 = np.ascontiguousarray(np.broadcast_to(prob.u_guess.T, (B, prob.N - 1, 12)))
+    ref = make_gpu(prob, B=B, x0=x0)
+    ref.begin_solve()
+    for _ in range(3):
+        ref.iterate()
+    s = make_gpu(prob, B=B, x0=x0)
+    x0_pin = torch.from_numpy(x0.copy()).pin_memory()
+    u_pin = torch.from_numpy(u0.copy()).pin_memory()
+    s.begin_solve()
+    ex = s.host_exchange()
+    ex.stage_inputs(x0_pin, u_pin)
+    for _ in range(3):
+        ex.apply_inputs()
+        s.iterate_linesearch()
+        ex.read_controls(u_pin)
+        s.iterate_finish_async()
+        ex.wait_controls()
+        ex.stage_inputs(x0_pin, u_pin)
+        n_active = s.iterate_wait()
+    assert n_active == int((ref.get_int(_lib.I_STATUS) == 0).sum())
+    for which in (_lib.X_BAR, _lib.U_BAR, _lib.K, _lib.KAPPA, _lib.COST):
+        assert np.array_equal(s.get(which), ref.get(which))
+    assert np.array_equal(u_pin.numpy(), ref.get(_lib.U_BAR))
