@@ -167,7 +167,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -384,7 +384,14 @@ def run_b200(args):
                              "achieved_GBps": (pb["backward"] + pb["derivs"] + pb["rollout"]) * value / world / 1e9,
                              "frac": (pb["backward"] + pb["derivs"] + pb["rollout"]) * value / world / 1e9 / hbm_peak},
                          "fp64": {"measured_peak_tflops": tf,
-                                  "backward_tflops": bwd_flops / (phase_ms["backward"] / K * 1e-3) / 1e12}},
+                                  "backward_tflops": bwd_flops / (phase_ms["backward"] / K * 1e-3) / 1e12,
+                                  # DMMAs the sweep issues per step at (36, 12): 681 for the products (8 x 8
+                                  # tile padding included) + 24 per Newton-Schulz pass, 2.8 passes on average
+                                  # (DESIGN.md section 3); 512 flop each, against the measured DMMA peak
+                                  "backward_dmma_issue_frac": (
+                                      (681 + 24 * 2.8) * 512.0 * T * active_per_step
+                                      / (phase_ms["backward"] / K * 1e-3) / 1e12 / tf["dmma"])
+                                  if (n, m) == (36, 12) and tf.get("dmma") else None}},
             "phase_ms_per_step": {k: v / K for k, v in phase_ms.items()},
             "ls_iters_mean_last_step": float(np.mean(ls)), "ls_parallel": solver.A,
             "trajectory_status": {"running": int((status == 0).sum()), "converged": int((status == 1).sum()),

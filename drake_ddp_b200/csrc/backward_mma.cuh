@@ -95,7 +95,10 @@ struct BwdMmaCfg {
   static constexpr bool TMA = ((n * n) % 2 == 0) && ((n * m) % 2 == 0) && (n % 2 == 0) && (m % 2 == 0);
   static constexpr bool EVEN = (n % 2 == 0) && (m % 2 == 0);  // C-fragment pairs never straddle rows
   static constexpr int even(int v) { return (v + 1) & ~1; }
-  static constexpr int MINB = (n <= 36) ? 4 : 3;  // CTAs per SM the register budget is sized for
+#ifndef DDP_BWD_MINB
+#define DDP_BWD_MINB 4
+#endif
+  static constexpr int MINB = (n <= 36) ? DDP_BWD_MINB : 3;  // CTAs per SM the register budget is sized for
   static_assert(2 * m <= n, "the Newton-Schulz scratch (2 m^2) lives in the Wu buffer (n m)");
   static_assert(n <= 64 && m <= 32, "vector warp keeps lx in two registers per lane and lu in one");
 };
