@@ -403,11 +403,11 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample of the same workload on the host cores (about 10-30 s of CPU work)
-            cpu_steps = 6
-            cv, procs, cdt, cunits = cpu_measure(args.horizon, cpu_steps, 1, per_proc=2)
+            cpu_steps, cpu_per_proc = 12, 8
+            cv, procs, cdt, cunits = cpu_measure(args.horizon, cpu_steps, 1, per_proc=cpu_per_proc)
             line["cpu_baseline"] = {
                 "value": cv, "unit": UNIT, "cores": procs, "kind": "port",
-                "sample": f"{2 * procs} trajectories (two per process, {procs} processes, 1 thread each) x {cpu_steps} "
+                "sample": f"{cpu_per_proc * procs} trajectories ({cpu_per_proc} per process, {procs} processes, 1 thread each) x {cpu_steps} "
                           f"iLQR iterations of the same C4 problem after 1 warm-up iteration "
                           f"({cunits} trajectory-iterations in {cdt:.1f} s wall)"}
             # cost vs reference: trajectory 0 re-solved by the oracle.  Compared after 2 iterations:

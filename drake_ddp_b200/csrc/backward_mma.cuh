@@ -12,8 +12,8 @@
 //   C1  K = Quu^-1 Qux      C2  Vxx <- Qxx - Qux' K     vector warp: kappa, dV, Vx
 // The fx / x_bar / u_bar tiles of step t-1 are prefetched into the other half of a double
 // buffer by 1-D bulk TMA (cp.async.bulk + mbarrier) while step t computes, fu is refilled as
-// soon as it is dead; when the tile sizes are not 16-byte multiples (odd n) the kernel falls
-// back to a cooperative copy.
+// soon as it is dead; when the tile sizes are not 16-byte multiples (odd n) the same schedule
+// runs on 8-byte cp.async copies issued by all threads.
 // Warp roles (warp id % 4 selects the SM sub-partition, and DMMA and DFMA share the fp64 pipe of
 // their sub-partition): warps 0-2 are DMMA warps, each owning a third of the column strips (or
 // row tiles) of every product, so an operand fragment loaded from shared memory feeds 2-6
@@ -406,11 +406,18 @@ backward_mma_kernel(Dev d) {
     mbar_expect_tx(&s.barFu, n * m * 8);
     tma_load_1d(s.Fu, gfu + (size_t)t * n * m, n * m * 8, &s.barFu);
   };
-  auto copy_tile = [&](int t, int buf) {    // all threads (fallback)
-    for (int i = tid; i < n * n; i += NT) s.Fx[buf][i] = gfx[(size_t)t * n * n + i];
-    for (int i = tid; i < n * m; i += NT) s.Fu[i] = gfu[(size_t)t * n * m + i];
-    for (int i = tid; i < n; i += NT) s.xb[buf][i] = gxb[(size_t)t * n + i];
-    for (int i = tid; i < m; i += NT) s.ub[buf][i] = gub[(size_t)t * m + i];
+  // odd n or m: tile starts are only 8-byte aligned, so the tiles travel as 8-byte cp.async
+  // copies issued by all threads (same double-buffer schedule as the bulk-TMA path)
+  auto cp8 = [&](double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+  };
+  auto copy_tile_async = [&](int t, int buf) {   // all threads
+    for (int i = tid; i < n * n; i += NT) cp8(&s.Fx[buf][i], gfx + (size_t)t * n * n + i);
+    for (int i = tid; i < n; i += NT) cp8(&s.xb[buf][i], gxb + (size_t)t * n + i);
+    for (int i = tid; i < m; i += NT) cp8(&s.ub[buf][i], gub + (size_t)t * m + i);
+  };
+  auto copy_fu_async = [&](int t) {              // all threads
+    for (int i = tid; i < n * m; i += NT) cp8(&s.Fu[i], gfu + (size_t)t * n * m + i);
   };
 
   // Deal the warp roles by CTA slot: the CTAs resident on one SM take distinct slots (per-SM
@@ -451,9 +458,15 @@ backward_mma_kernel(Dev d) {
   }
 #endif
   const bool issuer = (role == NMW) && (lane == 0);  // drives the TMA queue
-  if (C::TMA && issuer) {
-    issue_tile(T - 1, 0);
-    issue_fu(T - 1);
+  if (C::TMA) {
+    if (issuer) {
+      issue_tile(T - 1, 0);
+      issue_fu(T - 1);
+    }
+  } else {
+    copy_tile_async(T - 1, 0);
+    copy_fu_async(T - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   // Vx, Vxx <- terminal cost partials at x_bar[:, -1]            (ilqr.py:638, 203-204)
@@ -512,8 +525,14 @@ backward_mma_kernel(Dev d) {
       mbar_wait(&s.barFu, parityFu);
       parityFu ^= 1;
     } else {
-      copy_tile(t, buf);
+      // this step's tiles (and fu, issued after the previous step's phase B) have landed ...
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
+      // ... and the next step's start travelling into the other half
+      if (t > 0) {
+        copy_tile_async(t - 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
     }
     BWD_TICK(1);
     const double* Fx = s.Fx[buf];
@@ -643,7 +662,12 @@ backward_mma_kernel(Dev d) {
     BWD_TICK(6);
 
     // fu of this step is dead now: refill the single Fu buffer with the next step's tile
-    if (C::TMA && issuer && t > 0) issue_fu(t - 1);
+    if (C::TMA) {
+      if (issuer && t > 0) issue_fu(t - 1);
+    } else if (t > 0) {
+      copy_fu_async(t - 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // ---------------- phase C: K = Quu^-1 Qux ; Vxx = Qxx - Qux' K ; vector warp: kappa, dV, Vx --
     if (role < NMW) {
