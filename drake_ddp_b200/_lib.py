@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # symbols declared in include/ddp_b200.h
 SYMBOLS = [
     "ddp_last_error", "ddp_model_dims", "ddp_workspace_bytes", "ddp_create", "ddp_destroy",
-    "ddp_set_options", "ddp_set_keypoints", "ddp_set_cost", "ddp_set_target",
+    "ddp_set_options", "ddp_set_keypoints", "ddp_set_regularization", "ddp_set_cost", "ddp_set_target",
     "ddp_set_initial_state", "ddp_set_initial_guess", "ddp_reset", "ddp_begin_solve",
     "ddp_iterate", "ddp_iterate_linesearch", "ddp_iterate_finish_async", "ddp_iterate_wait", "ddp_solve",
     "ddp_run_phase", "ddp_get",
@@ -91,6 +91,7 @@ def lib():
     L.ddp_reset.argtypes = [c_vp]
     L.ddp_begin_solve.argtypes = [c_vp]
     L.ddp_mpc_shift.argtypes = [c_vp, c_int]
+    L.ddp_set_regularization.argtypes = [c_vp, c_dbl]
     L.ddp_iterate.argtypes = [c_vp, ip]
     L.ddp_iterate_linesearch.argtypes = [c_vp]
     L.ddp_iterate_finish_async.argtypes = [c_vp]

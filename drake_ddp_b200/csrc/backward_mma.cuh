@@ -580,8 +580,8 @@ backward_mma_kernel(Dev d) {
             acc, tg, [&](int kk) { return pa[kk * 4 * m]; }, [&](int kk) { return pb[kk * 4 * m]; });
         const int r = r8 + g, c = c8 + 2 * tg;
         if (r < m) {
-          if (c < m) s.Quu[r * m + c] = 2.0 * R[r * m + c] + acc[0];
-          if (c + 1 < m) s.Quu[r * m + c + 1] = 2.0 * R[r * m + c + 1] + acc[1];
+          if (c < m) s.Quu[r * m + c] = 2.0 * R[r * m + c] + acc[0] + ((r == c) ? d.quu_reg : 0.0);
+          if (c + 1 < m) s.Quu[r * m + c + 1] = 2.0 * R[r * m + c + 1] + acc[1] + ((r == c + 1) ? d.quu_reg : 0.0);
         }
       }
       asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");

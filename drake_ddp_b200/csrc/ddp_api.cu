@@ -527,6 +527,15 @@ int ddp_set_options(ddp_solver_t* s, double delta, double beta, double gamma) {
   return 0;
 }
 
+int ddp_set_regularization(ddp_solver_t* s, double quu_reg) {
+  if (!(quu_reg >= 0.0)) {
+    g_err = "quu_reg must be >= 0";
+    return DDP_ERR_ARG;
+  }
+  s->d.quu_reg = quu_reg;
+  return 0;
+}
+
 int ddp_set_keypoints(ddp_solver_t* s, int method, int minN, int maxN, double jerk_threshold,
                       double iterative_error_threshold) {
   if (method < 0 || method > 2) {

@@ -17,6 +17,7 @@ namespace ddp {
 struct Dev {
   int n, m, N, T, B, A, n_eps, diag_cost;
   double delta, gamma;
+  double quu_reg;  // added to the diagonal of Quu before it is inverted (0: the reference's behaviour)
   const double* params;
   const double *Q, *R, *Qf, *x_nom, *x0, *eps_table;
   double *x_bar, *u_bar, *K, *kappa, *dV, *fx, *fu;
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
       const int r = idx / m, q = idx % m;
       double a = 2.0 * R[idx];
       for (int i = 0; i < n; ++i) a = fma(s.Fu[i * m + r], s.Wu[i * m + q], a);
-      s.Quu[idx] = a;
+      s.Quu[idx] = (r == q) ? a + d.quu_reg : a;
     }
     __syncthreads();
     if (tid < 32) invert_warp<m>(s.Quu, s.Inv);                 // ilqr.py:655

@@ -103,6 +103,10 @@ class BatchedILQR:
                                              int(cfg.maxN), float(cfg.jerk_threshold),
                                              float(cfg.iterative_error_threshold)), "ddp_set_keypoints")
 
+    def set_regularization(self, quu_reg: float):
+        """Extension: Quu + quu_reg*I is inverted in the backward pass (0 = the reference, ilqr.py:654-655)."""
+        _lib.check(self._L.ddp_set_regularization(self._h, float(quu_reg)), "ddp_set_regularization")
+
     def set_cost(self, Q, R, Qf):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         R = np.ascontiguousarray(R, dtype=np.float64)

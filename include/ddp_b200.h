@@ -112,6 +112,9 @@ int ddp_set_options(ddp_solver_t* s, double delta, double beta, double gamma);
 /* derivs_keypoint_method (ilqr.py:97-100). */
 int ddp_set_keypoints(ddp_solver_t* s, int method, int minN, int maxN, double jerk_threshold,
                       double iterative_error_threshold);
+/* Extension (no counterpart in the reference, which inverts Quu as is,
+ * ilqr.py:654-655): Quu <- Quu + quu_reg * I before the inverse.  Default 0 = reference. */
+int ddp_set_regularization(ddp_solver_t* s, double quu_reg);
 /* SetRunningCost / SetTerminalCost (ilqr.py:120-146); host pointers, shared by the batch. */
 int ddp_set_cost(ddp_solver_t* s, const double* Q, const double* R, const double* Qf);
 /* SetTargetState (ilqr.py:111-118); x_nom is [n] (per_trajectory=0) or [B][n]. */

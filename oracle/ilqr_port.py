@@ -86,11 +86,12 @@ class IterRecord:
 
 
 class IlqrOracle:
-    def __init__(self, dyn, num_timesteps, delta=1e-2, beta=0.95, gamma=0.0, keypoints=None):
+    def __init__(self, dyn, num_timesteps, delta=1e-2, beta=0.95, gamma=0.0, keypoints=None, quu_reg=0.0):
         """ilqr.py:21-100.  ``dyn`` has n, m, step(x,u), jac(x,u)."""
         self.dyn = dyn
         self.N, self.n, self.m = int(num_timesteps), dyn.n, dyn.m
         self.delta, self.beta, self.gamma = delta, beta, gamma
+        self.quu_reg = float(quu_reg)   # extension (not in the reference): Quu + quu_reg*I; 0 = ilqr.py:654
         T, n, m = self.N - 1, self.n, self.m
         self.x0 = np.zeros(n)
         self.x_nom = np.zeros(n)
@@ -220,6 +221,8 @@ class IlqrOracle:
             Qu = lu + fu.T @ Vx
             Qxx = 2 * Q + fx.T @ Vxx @ fx
             Quu = 2 * R + fu.T @ Vxx @ fu
+            if self.quu_reg:
+                Quu = Quu + self.quu_reg * np.eye(self.m)
             Quu_inv = np.linalg.inv(Quu)
             Qux = fu.T @ Vxx @ fx
             self.kappa[t] = Quu_inv @ Qu

@@ -429,3 +429,39 @@ def test_split_iterate_and_host_exchange_equal_iterate():
     for which in (_lib.X_BAR, _lib.U_BAR, _lib.K, _lib.KAPPA, _lib.COST):
         assert np.array_equal(s.get(which), ref.get(which))
     assert np.array_equal(u_pin.numpy(), ref.get(_lib.U_BAR))
+
+
+def test_quu_regularization_extension_matches_oracle():
+    """ddp_set_regularization (SURVEY 8f-4 extension, default 0 = reference): Quu + mu*I in the
+    backward pass, against the oracle port with the same mu; mu = 0 stays bit-identical to the
+    default path."""
+    prob = problems.quadruped(40)
+    for mu in (0.0, 1e-2):
+        s = make_gpu(prob)
+        s.set_regularization(mu)
+        o = make_oracle(prob)
+        o.quu_reg = mu
+        s.begin_solve()
+        L = np.inf
+        for _ in range(3):
+            s.iterate()
+            rec = o.iterate(L)
+            L = rec.L
+            assert abs(s.cost[0] - rec.L) <= COST_RTOL * abs(rec.L)
+            assert int(s.get_int(_lib.I_LS_ITERS)[0]) == rec.ls_iters
+            assert relerr(s.get(_lib.K)[0], o.K) < GAIN_RTOL
+        if mu == 0.0:
+            ref = make_gpu(prob)
+            ref.begin_solve()
+            for _ in range(3):
+                ref.iterate()
+            assert np.array_equal(ref.get(_lib.K), s.get(_lib.K))
+    small = problems.acrobot(40)           # scalar backward kernel (n < 16)
+    s = make_gpu(small)
+    s.set_regularization(0.5)
+    o = make_oracle(small)
+    o.quu_reg = 0.5
+    s.begin_solve()
+    s.iterate()
+    o.iterate(np.inf)
+    assert relerr(s.get(_lib.K)[0], o.K) < GAIN_RTOL
