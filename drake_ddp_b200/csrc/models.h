@@ -409,7 +409,7 @@ struct Quadruped {
 // Same parameter vector as Quadruped.
 struct QuadrupedQuat {
   static constexpr int n = 37, m = 12, np = 20;
-  static constexpr int COOP = 1;
+  static constexpr int COOP = 4;  // step_coop: one leg per lane of a 4-lane group
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     typedef Quadruped Qd;
@@ -499,6 +499,102 @@ struct QuadrupedQuat {
       xn[25 + i] = vj[i];
     }
   }
+
+#if defined(__CUDACC__)
+  // The same map evaluated by a 4-lane group: lane l computes leg l, loads are combined with the
+  // butterfly (leg0 + leg1) + (leg2 + leg3), joint accelerations are exchanged with shuffles;
+  // everything else is evaluated redundantly.  Bit-identical to step<double>().
+  __device__ __forceinline__ static void step_coop(int lane, unsigned mask, int gbase, const double* x,
+                                                   const double* u, double* xn, const double* p) {
+    typedef Quadruped Qd;
+    const int sub = (int)p[1];
+    const double h = p[0] / sub;
+    const double Ix = p[3], Iy = p[4], Iz = p[5];
+    double qt[4], pos[3], qj[12], w[3], vl[3], vj[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qt[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      pos[i] = x[4 + i];
+      w[i] = x[19 + i];
+      vl[i] = x[22 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      qj[i] = x[7 + i];
+      vj[i] = x[25 + i];
+    }
+    const double ua = Qd::pick4(lane, u[0], u[3], u[6], u[9]);
+    const double uh = Qd::pick4(lane, u[1], u[4], u[7], u[10]);
+    const double uk = Qd::pick4(lane, u[2], u[5], u[8], u[11]);
+    const double sx = (lane < 2) ? 1.0 : -1.0, sd = (lane & 1) ? 1.0 : -1.0;
+    for (int it = 0; it < sub; ++it) {
+      double nn = sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+      double a = qt[0] / nn, b = qt[1] / nn, c = qt[2] / nn, d = qt[3] / nn;
+      Qd::BasePose<double> B;
+      B.R00 = 1.0 - 2.0 * (c * c + d * d); B.R01 = 2.0 * (b * c - a * d); B.R02 = 2.0 * (b * d + a * c);
+      B.R10 = 2.0 * (b * c + a * d); B.R11 = 1.0 - 2.0 * (b * b + d * d); B.R12 = 2.0 * (c * d - a * b);
+      B.R20 = 2.0 * (b * d - a * c); B.R21 = 2.0 * (c * d + a * b); B.R22 = 1.0 - 2.0 * (b * b + c * c);
+      B.sr = 0.0; B.cr = 1.0; B.sp = 0.0; B.cp = 1.0;
+      double vloc[6];
+      vloc[0] = vl[0]; vloc[1] = vl[1]; vloc[2] = vl[2];
+      vloc[3] = B.R00 * w[0] + B.R10 * w[1] + B.R20 * w[2];
+      vloc[4] = B.R01 * w[0] + B.R11 * w[1] + B.R21 * w[2];
+      vloc[5] = B.R02 * w[0] + B.R12 * w[1] + B.R22 * w[2];
+      Qd::LegOut<double> o;
+      Qd::leg(sx, sd, Qd::pick4(lane, qj[0], qj[3], qj[6], qj[9]), Qd::pick4(lane, qj[1], qj[4], qj[7], qj[10]),
+              Qd::pick4(lane, qj[2], qj[5], qj[8], qj[11]), Qd::pick4(lane, vj[0], vj[3], vj[6], vj[9]),
+              Qd::pick4(lane, vj[1], vj[4], vj[7], vj[10]), Qd::pick4(lane, vj[2], vj[5], vj[8], vj[11]), ua, uh, uk,
+              pos[2], vloc, B, p, o);
+      double f[6] = {o.Fx, o.Fy, o.Fz, o.Tx, o.Ty, o.Tz};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        f[k] += __shfl_xor_sync(mask, f[k], 1);
+        f[k] += __shfl_xor_sync(mask, f[k], 2);
+      }
+      double aj[12];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        aj[3 * l] = __shfl_sync(mask, o.a0, gbase + l);
+        aj[3 * l + 1] = __shfl_sync(mask, o.a1, gbase + l);
+        aj[3 * l + 2] = __shfl_sync(mask, o.a2, gbase + l);
+      }
+      double ab0 = (f[3] - (Iz - Iy) * vloc[4] * vloc[5]) / Ix;
+      double ab1 = (f[4] - (Ix - Iz) * vloc[5] * vloc[3]) / Iy;
+      double ab2 = (f[5] - (Iy - Ix) * vloc[3] * vloc[4]) / Iz;
+      w[0] = w[0] + h * (B.R00 * ab0 + B.R01 * ab1 + B.R02 * ab2);
+      w[1] = w[1] + h * (B.R10 * ab0 + B.R11 * ab1 + B.R12 * ab2);
+      w[2] = w[2] + h * (B.R20 * ab0 + B.R21 * ab1 + B.R22 * ab2);
+      vl[0] = vl[0] + h * (f[0] / p[2]);
+      vl[1] = vl[1] + h * (f[1] / p[2]);
+      vl[2] = vl[2] + h * (f[2] / p[2] - p[19]);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) vj[i] = vj[i] + h * aj[i];
+      double q0 = qt[0], q1 = qt[1], q2 = qt[2], q3 = qt[3];
+      qt[0] = q0 + (0.5 * h) * (-(w[0] * q1) - w[1] * q2 - w[2] * q3);
+      qt[1] = q1 + (0.5 * h) * (w[0] * q0 + w[1] * q3 - w[2] * q2);
+      qt[2] = q2 + (0.5 * h) * (w[1] * q0 + w[2] * q1 - w[0] * q3);
+      qt[3] = q3 + (0.5 * h) * (w[2] * q0 + w[0] * q2 - w[1] * q1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pos[i] = pos[i] + h * vl[i];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) qj[i] = qj[i] + h * vj[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn[i] = qt[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      xn[4 + i] = pos[i];
+      xn[19 + i] = w[i];
+      xn[22 + i] = vl[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      xn[7 + i] = qj[i];
+      xn[25 + i] = vj[i];
+    }
+  }
+#endif
 };
 
 // ------------------------------------------------------------------------------
