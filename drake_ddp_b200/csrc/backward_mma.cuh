@@ -344,12 +344,16 @@ static_assert(sizeof(BwdMmaSmem<36, 12>) <= 57088, "backward_mma_kernel: shared 
 #endif
 #ifdef DDP_BWD_PROFILE
 // per-phase cycle totals of one DMMA warp and the vector warp of two CTAs (first / second wave)
-__device__ long long g_bwd_prof[2][2][16];
+__device__ long long g_bwd_prof[2][4][16];   // [cta][role][phase]
 
+// the clock is read after a shared-memory load so that it cannot run ahead of a barrier the
+// warp has arrived at but not yet passed (BAR.SYNC.DEFER_BLOCKING)
 #define BWD_TICK(i)                                                     \
   do {                                                                  \
     if (prof_on) {                                                      \
-      const long long now_ = clock64();                                 \
+      const int dep_ = *reinterpret_cast<volatile int*>(&s.slot);       \
+      long long now_;                                                   \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_) : "r"(dep_) : "memory"); \
       prof_acc[i] += now_ - prof_last;                                  \
       prof_last = now_;                                                 \
     }                                                                   \
@@ -511,8 +515,8 @@ backward_mma_kernel(Dev d) {
   const bool fence_never = (DDP_BWD_FENCE == 2) ? (tid == d.N + 100000) : (d.N < 0);
 #endif
 #ifdef DDP_BWD_PROFILE
-  const int prof_cta = (b == 5) ? 0 : ((b == 800) ? 1 : -1);
-  const bool prof_on = prof_cta >= 0 && lane == 0 && (role == 1 || role == NMW);
+  const int prof_cta = (b == 5) ? 0 : ((b == 100) ? 1 : -1);
+  const bool prof_on = prof_cta >= 0 && lane == 0;
   long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_last = clock64();
 #endif
@@ -548,16 +552,21 @@ backward_mma_kernel(Dev d) {
         o.s4[i] = in_fx ? 4 * n : 4 * m;
       };
       auto vxx_rows = [&](OpS<GN, 1>& o, int i, int r) { o.p[i] = s.Vxx + min(r, n - 1) * n + tg; };
+      // (the epilogues are written branch-free -- selected pointers, predicated stores: a
+      // divergent branch per tile costs more than the DMMAs of the tile)
       auto store_w = [&](int r, int c, double v0, double v1) {   // columns of [W | Wu]
-        if (r >= n) return;
+        const bool rok = r < n;
         if (EVEN) {  // c even, n even: the pair is inside W or inside Wu
-          if (c < n) *reinterpret_cast<double2*>(&s.W[r * LDW + c]) = make_double2(v0, v1);
-          else if (c < n + m) *reinterpret_cast<double2*>(&s.WuKt[r * m + (c - n)]) = make_double2(v0, v1);
+          const bool in_w = c < n;
+          double* dst = in_w ? (s.W + r * LDW + c) : (s.WuKt + r * m + (c - n));
+          if (rok && c < n + m) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
         } else {
-          if (c < n) s.W[r * LDW + c] = v0;
-          else if (c < n + m) s.WuKt[r * m + (c - n)] = v0;
-          if (c + 1 < n) s.W[r * LDW + c + 1] = v1;
-          else if (c + 1 < n + m) s.WuKt[r * m + (c + 1 - n)] = v1;
+          if (rok) {
+            if (c < n) s.W[r * LDW + c] = v0;
+            else if (c < n + m) s.WuKt[r * m + (c - n)] = v0;
+            if (c + 1 < n) s.W[r * LDW + c + 1] = v1;
+            else if (c + 1 < n + m) s.WuKt[r * m + (c + 1 - n)] = v1;
+          }
         }
       };
       auto stacked_tail = [&](OpD<TS - TF>& o, int i, int c) { stacked_slot(o, i, c); };
@@ -593,7 +602,9 @@ backward_mma_kernel(Dev d) {
       asm volatile("bar.sync 1, %0;" ::"r"(NMW * 32) : "memory");
       BWD_TICK(4);
       // ---- B: [Qxx Qx ; Qux Qu] = [lxx . ; 0 .] + S' [W | Vx]          (ilqr.py:651-653,656) -----
-      // warp w owns its group of S' row tiles, all column strips of [W | Vx]
+      // warp w owns its group of S' row tiles, all column strips of [W | Vx].  (Claiming single
+      // row tiles from a ticket counter instead, to even out the different progress of the three
+      // sub-partitions under contention, was measured slower: 3.79 vs 3.66 ms -- less operand reuse.)
       {
         int r0, nr;
         split3<TS>(role, r0, nr);
@@ -601,26 +612,22 @@ backward_mma_kernel(Dev d) {
             r0, nr, 0, TW, g, tg, stacked_slot,
             [&](OpS<TW, LDW>& o, int j, int c) { o.p[j] = s.W + tg * LDW + min(c, LDW - 1); },
             [&](int r, int c, double v0, double v1) {
-              if (r >= n + m) return;
-              if (c == n) {            // column n: fx' Vx, fu' Vx
-                if (r < n) s.QxM[r] = v0;
-                else s.QuM[r - n] = v0;
-              } else if (!EVEN && c + 1 == n) {
-                if (r < n) s.QxM[r] = v1;
-                else s.QuM[r - n] = v1;
+              const bool rok = ((n + m) % 8 == 0) || (r < n + m);
+              const bool isx = r < n;                  // Qxx row, else Qux row r - n
+              // column n: fx' Vx, fu' Vx
+              double* vec = isx ? (s.QxM + r) : (s.QuM + (r - n));
+              if (rok && c == n) *vec = v0;
+              if (!EVEN && rok && c + 1 == n) *vec = v1;
+              if (diag) {
+                const double qd = s.Qd2[isx ? r : 0];
+                v0 += (isx && r == c) ? qd : 0.0;
+                v1 += (isx && r == c + 1) ? qd : 0.0;
+              } else if (isx) {
+                if (c < n) v0 += 2.0 * Q[r * n + c];
+                if (c + 1 < n) v1 += 2.0 * Q[r * n + c + 1];
               }
-              if (r < n) {
-                if (diag) {
-                  if (r == c) v0 += s.Qd2[r];
-                  if (r == c + 1) v1 += s.Qd2[r];
-                } else {
-                  if (c < n) v0 += 2.0 * Q[r * n + c];
-                  if (c + 1 < n) v1 += 2.0 * Q[r * n + c + 1];
-                }
-                st_pair<EVEN>(s.Vxx, r * n + c, c < n, c + 1 < n, v0, v1);
-              } else {
-                st_pair<EVEN>(s.Qux, (r - n) * n + c, c < n, c + 1 < n, v0, v1);
-              }
+              double* dst = isx ? (s.Vxx + r * n) : (s.Qux + (r - n) * n);
+              st_pair<EVEN>(dst, c, rok && c < n, rok && c + 1 < n, v0, v1);
             });
       }
       BWD_TICK(5);
@@ -679,9 +686,9 @@ backward_mma_kernel(Dev d) {
             [&](OpS<TM, 1>& o, int i, int r) { o.p[i] = s.QuuInv + min(r, m - 1) * m + tg; },
             [&](OpS<C1R, n>& o, int j, int c) { o.p[j] = s.Qux + tg * n + min(c, n - 1); },
             [&](int r, int c, double v0, double v1) {
-              if (r >= m) return;
-              st_pair<EVEN>(s.WuKt, r * n + c, c < n, c + 1 < n, v0, v1);
-              st_pair<EVEN>(gK, r * n + c, c < n, c + 1 < n, v0, v1);
+              const bool rok = r < m;
+              st_pair<EVEN>(s.WuKt, r * n + c, rok && c < n, rok && c + 1 < n, v0, v1);
+              st_pair<EVEN>(gK, r * n + c, rok && c < n, rok && c + 1 < n, v0, v1);
             });
       }
       BWD_TICK(7);
@@ -696,16 +703,14 @@ backward_mma_kernel(Dev d) {
             [&](OpS<TN, n>& o, int i, int r) { o.p[i] = s.Qux + tg * n + min(r, n - 1); },
             [&](OpS<GN, n>& o, int j, int c) { o.p[j] = s.WuKt + tg * n + min(c, n - 1); },
             [&](int r, int c, double v0, double v1) {
-              if (r >= n) return;
               if (EVEN) {
-                if (c < n) {
-                  double2* p = reinterpret_cast<double2*>(&s.Vxx[r * n + c]);
-                  double2 o = *p;
-                  o.x -= v0;
-                  o.y -= v1;
-                  *p = o;
-                }
-              } else {
+                const bool ok = r < n && c < n;
+                double2* p = reinterpret_cast<double2*>(&s.Vxx[ok ? (r * n + c) : 0]);
+                double2 o = *p;
+                o.x -= v0;
+                o.y -= v1;
+                if (ok) *p = o;
+              } else if (r < n) {
                 if (c < n) s.Vxx[r * n + c] -= v0;
                 if (c + 1 < n) s.Vxx[r * n + c + 1] -= v1;
               }
@@ -768,7 +773,7 @@ backward_mma_kernel(Dev d) {
   if (tid == 0 && slot_word) atomicAnd(slot_word, ~(1 << slot));
 #ifdef DDP_BWD_PROFILE
   if (prof_on)
-    for (int i = 0; i < 12; ++i) g_bwd_prof[prof_cta][role == NMW ? 1 : 0][i] = prof_acc[i];
+    for (int i = 0; i < 12; ++i) g_bwd_prof[prof_cta][role][i] = prof_acc[i];
 #endif
 }
 

@@ -794,15 +794,15 @@ int ddp_debug_roll_profile(long long* out16) {
 // debug builds only: per-phase cycle totals recorded by backward_mma_kernel
 int ddp_debug_bwd_profile(long long* out64) {
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpyFromSymbol(out64, ddp::g_bwd_prof, sizeof(long long) * 64));
+  CK(cudaMemcpyFromSymbol(out64, ddp::g_bwd_prof, sizeof(long long) * 128));
   int fb = 0, zero = 0;
   CK(cudaMemcpyFromSymbol(&fb, ddp::g_bwd_fallbacks, sizeof(int)));
   CK(cudaMemcpyToSymbol(ddp::g_bwd_fallbacks, &zero, sizeof(int)));
-  out64[63] = fb;
+  out64[127] = fb;
   int ps = 0;
   CK(cudaMemcpyFromSymbol(&ps, ddp::g_bwd_passes, sizeof(int)));
   CK(cudaMemcpyToSymbol(ddp::g_bwd_passes, &zero, sizeof(int)));
-  out64[62] = ps;
+  out64[126] = ps;
   return 0;
 }
 #endif

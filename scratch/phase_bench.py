@@ -59,15 +59,15 @@ for name in phases:
 print(out)
 if os.environ.get("PB_PROF"):
     import ctypes
-    buf = (ctypes.c_longlong * 64)()
+    buf = (ctypes.c_longlong * 128)()
     _lib.lib().ddp_debug_bwd_profile(buf)
-    print('gauss-jordan fallbacks (all launches):', buf[63], 'of', B * (N - 1), 'per launch; newton passes (all launches):', buf[62])
-    a = np.array(buf[:], dtype=np.int64).reshape(2, 2, 16)[:, :, :11]
+    print('gauss-jordan fallbacks (all launches):', buf[127], 'of', B * (N - 1), 'per launch; newton passes (all launches):', buf[126])
+    a = np.array(buf[:], dtype=np.int64).reshape(2, 4, 16)[:, :, :11]
     names = ["loop", "mbar", "A1+bar|lxlu", "A2|waitQuu", "A3+bar|inv", "B", "S1", "C1", "bar1", "C2|vecC", "S2"]
     for cta in range(2):
-        for w in range(2):
+        for w in range(4):
             tot = a[cta, w].sum()
-            print("cta", cta, "dmma-warp" if w == 0 else "vector   ", "cycles/step", int(tot / (N - 1)),
+            print("cta", cta, f"dmma role {w}" if w < 3 else "vector warp", "cycles/step", int(tot / (N - 1)),
                   {nm: int(v / (N - 1)) for nm, v in zip(names, a[cta, w])})
 
 if os.environ.get("PB_ROLLPROF"):
