@@ -6,7 +6,7 @@ from drake_ddp_b200 import problems, _lib
 from drake_ddp_b200.ilqr import BatchedILQR
 name = os.environ.get("SAN_MODEL", "quadruped")
 prob = getattr(problems, name)(12)
-B = 3
+B = int(os.environ.get("SAN_B", "3"))
 s = BatchedILQR(prob.system, prob.N, batch=B, delta=prob.delta, beta=prob.beta, gamma=prob.gamma,
                 ls_parallel=int(os.environ.get("SAN_A", "8")))
 s.set_cost(prob.Q, prob.R, prob.Qf); s.set_target(prob.x_nom)
