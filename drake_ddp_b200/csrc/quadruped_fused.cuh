@@ -10,11 +10,10 @@
 //      templates as the rollout, 64 dual leg evaluations per substep instead of 192; each of
 //      the 15 sines / cosines a substep needs is computed by one lane and shared by shuffle;
 //   2. every lane scatters its derivatives straight into the substep Jacobian in shared memory
-//      (base rows are summed over the legs with the same two-stage butterfly the rollout uses),
-//      the integrator rows follow element-wise (QuadJac::dq_elem);
+//      (base rows are summed over the legs with the same two-stage butterfly the rollout uses);
 //   3. the two substeps are chained on the fp64 tensor pipe: only the velocity rows need a
-//      product, v2 = Dv2[:, :36] D1 + [0 | Dv2[:, 36:]] (162 DMMAs), the position rows follow
-//      from q+ = q + h N(q) v+ element-wise.
+//      product, and with the position rows of substep 1 folded in (D1q = E1 + h N1 D1v) it is
+//      18 x 18 x 48 (90 DMMAs); the position rows follow from q+ = q + h N(q) v+ element-wise.
 // One warp per point, all intermediates in that warp's slice of shared memory; fx, fu are
 // written once.  Exact derivative of Quadruped::step: checked against the generic AD kernel
 // and the host AD (tests/test_gpu_parity.py).  Two substeps only (the model's setting); other
@@ -36,13 +35,20 @@ constexpr int kQfWarps = QF_WARPS;   // warps (points in flight) per CTA
 #endif
 
 struct QfWarpSmem {
-  double D1[36 * kQfLd];      // substep-1 Jacobian d(q1, v1)/d(q, v, u), 36 x 48
+  double D1v[20 * kQfLd];     // velocity rows of the substep-1 Jacobian d v1/d(q, v, u), 18 x 48 (+2 pad rows)
   double D2v[18 * kQfLd];     // velocity rows of the substep-2 Jacobian, 18 x 48
   double v2s[3 * 48];         // rows 3..5 of the chained velocity rows (Euler-rate coupling)
   double st[3][36];           // x_t, state after substep 1, after substep 2
 };
 
+#ifndef QF_MAXNREG
+#define QF_MAXNREG 0
+#endif
+#if QF_MAXNREG
+__global__ void __maxnreg__(QF_MAXNREG)
+#else
 __global__ void __launch_bounds__(kQfWarps * 32, QF_MINB)
+#endif
 quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   typedef Quadruped Qd;
   typedef Dual<2> D2;
@@ -65,11 +71,11 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
 
   // the Jacobian buffers keep their zero pattern across points: only the structural nonzeros
   // are rewritten.  The direct u -> joint acceleration terms are constant.
-  for (int i = lane; i < 36 * LD; i += 32) s.D1[i] = 0.0;
+  for (int i = lane; i < 20 * LD; i += 32) s.D1v[i] = 0.0;
   for (int i = lane; i < 18 * LD; i += 32) s.D2v[i] = 0.0;
   __syncwarp();
   if (lane < 12) {
-    s.D1[(18 + 6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
+    s.D1v[(6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
     s.D2v[(6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
   }
   __syncwarp();
@@ -123,7 +129,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
     for (int sub = 0; sub < 2; ++sub) {
       const double* xin = s.st[sub];
       double* xout = s.st[sub + 1];
-      double* Dv = (sub == 0) ? (s.D1 + 18 * LD) : s.D2v;   // 18 x 48 velocity rows of this substep
+      double* Dv = (sub == 0) ? s.D1v : s.D2v;   // 18 x 48 velocity rows of this substep
       // ---- dual evaluation of this lane's leg along its two local directions -----------------
       auto seed = [&](double v, int j) {
         D2 r;
@@ -245,16 +251,40 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       __syncwarp();
       if (sub == 0) {
         if (nok) nxt = fetch_pt(nb, nt);   // next point's state and controls: consumed a substep later
-        // position rows of D1 from its finished velocity rows (QuadJac::dq_elem)
-        for (int r = 0; r < 18; ++r)
-          for (int c = lane; c < 48; c += 32)
-            s.D1[r * LD + c] = QuadJac::dq_elem(s.D1 + 18 * LD, LD, trig[0][0], trig[0][1], trig[0][2], trig[0][3],
-                                                xout + 18, h, r, c);
-        __syncwarp();
       }
     }
 
-    // ---- chain: v2 = Dv2[:, :36] D1 + [0 | Dv2[:, 36:]] on the tensor pipe -----------------------
+    // ---- chain ----------------------------------------------------------------------------------
+    // With Dv2 = [Aq | Av | Au] (18 x (18+18+12)), D1v the velocity rows of substep 1 and
+    // D1q = E1 + h N1 D1v its position rows (E1 = [I + h M1 | 0 | 0], N1 the Euler-rate matrix):
+    //   v2 = Aq D1q + Av D1v + [0 0 Au] = [Aq E1 | 0 | Au] + (Av + h Aq N1) D1v,
+    // so the position rows of D1 are never formed and the product has K = 18: 90 DMMAs.
+    // M1 and N1 differ from the identity only in rows / columns 3..5 (roll, pitch, yaw).
+    const double* D1v = s.D1v;
+    {
+      const double sr = trig[0][0], cr = trig[0][1], sp = trig[0][2], cp = trig[0][3];
+      const double tp = sp / cp, w4 = s.st[1][22], w5 = s.st[1][23];
+      const double wyz = sr * w4 + cr * w5, wr = cr * w4 - sr * w5;
+      const double N34 = tp * sr, N35 = tp * cr, N44 = cr, N45 = -sr, N54 = sr / cp, N55 = cr / cp;
+      // A' = Av + h Aq N1, in place of Av
+      for (int idx = lane; idx < 18 * 18; idx += 32) {
+        const int r = idx / 18, jc = idx - 18 * r;
+        const double* row = s.D2v + r * LD;
+        double aqn = row[jc];
+        if (jc == 4) aqn = row[3] * N34 + row[4] * N44 + row[5] * N54;
+        if (jc == 5) aqn = row[3] * N35 + row[4] * N45 + row[5] * N55;
+        s.D2v[r * LD + 18 + jc] = row[18 + jc] + h * aqn;
+      }
+      __syncwarp();
+      // Aq E1, in place of Aq (columns 3 and 4 only)
+      if (lane < 18) {
+        double* row = s.D2v + lane * LD;
+        const double a3 = row[3], a4 = row[4], a5 = row[5];
+        row[3] = a3 * (1.0 + h * tp * wr) + a4 * (-h * wyz) + a5 * (h * wr / cp);
+        row[4] = a3 * (h * wyz / (cp * cp)) + a4 + a5 * (h * wyz * sp / (cp * cp));
+      }
+      __syncwarp();
+    }
     double acc[3][6][2];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
@@ -263,15 +293,16 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
     {
       const double* pa[3];
 #pragma unroll
-      for (int mt = 0; mt < 3; ++mt) pa[mt] = s.D2v + min(8 * mt + g, 17) * LD + tg;
-      const double* pb = s.D1 + tg * LD + g;
+      for (int mt = 0; mt < 3; ++mt) pa[mt] = s.D2v + min(8 * mt + g, 17) * LD + 18 + tg;
+      const double* pb = D1v + tg * LD + g;
 #pragma unroll
-      for (int kk = 0; kk < 9; ++kk) {
+      for (int kk = 0; kk < 5; ++kk) {
+        const bool kin = (kk < 4) || (tg < 2);   // k = 4 kk + tg < 18
         double a[3], bb[6];
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt) a[mt] = pa[mt][4 * kk];
+        for (int mt = 0; mt < 3; ++mt) a[mt] = kin ? pa[mt][4 * kk] : 0.0;
 #pragma unroll
-        for (int nt = 0; nt < 6; ++nt) bb[nt] = pb[4 * kk * LD + 8 * nt];
+        for (int nt = 0; nt < 6; ++nt) bb[nt] = kin ? pb[4 * kk * LD + 8 * nt] : 0.0;
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
@@ -292,7 +323,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         for (int nt = 0; nt < 6; ++nt) {
           const int c = 8 * nt + 2 * tg;
           double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
-          if (c >= 36) {
+          if (c < 18 || c >= 36) {   // + [Aq E1 | 0 | Au]
             v0 += s.D2v[r * LD + c];
             v1 += s.D2v[r * LD + c + 1];
           }
@@ -300,8 +331,10 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
           if (r >= 3 && r < 6) {   // Euler-rate rows need rows 3..5 together: stage them
             s.v2s[(r - 3) * 48 + c] = v0;
             s.v2s[(r - 3) * 48 + c + 1] = v1;
-          } else {                 // q+ = q + h v+
-            store2(r, c, s.D1[r * LD + c] + h * v0, s.D1[r * LD + c + 1] + h * v1);
+          } else {                 // q2 = D1q + h v2 with D1q = I + h D1v on these rows
+            const double q0 = ((c == r) ? 1.0 : 0.0) + h * D1v[r * LD + c];
+            const double q1 = ((c + 1 == r) ? 1.0 : 0.0) + h * D1v[r * LD + c + 1];
+            store2(r, c, q0 + h * v0, q1 + h * v1);
           }
         }
       }
@@ -312,8 +345,26 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       const double sr = trig[1][0], cr = trig[1][1], sp = trig[1][2], cp = trig[1][3];
       const double tp = sp / cp, wy = s.st[2][22], wz = s.st[2][23];
       const double wyz = sr * wy + cr * wz, wr = cr * wy - sr * wz;
+      // D1q rows 3..5 = E1 + h N1 D1v with the Euler-rate matrices of substep 1 (QuadJac::dq_elem)
+      const double sr1 = trig[0][0], cr1 = trig[0][1], sp1 = trig[0][2], cp1 = trig[0][3];
+      const double tp1 = sp1 / cp1, wy1 = s.st[1][22], wz1 = s.st[1][23];
+      const double wyz1 = sr1 * wy1 + cr1 * wz1, wr1 = cr1 * wy1 - sr1 * wz1;
       for (int c = lane; c < 48; c += 32) {
-        const double d3 = s.D1[3 * LD + c], d4 = s.D1[4 * LD + c], d5 = s.D1[5 * LD + c];
+        const double f3 = D1v[3 * LD + c], f4 = D1v[4 * LD + c], f5 = D1v[5 * LD + c];
+        double d3 = h * (f3 + tp1 * (sr1 * f4 + cr1 * f5));
+        double d4 = h * (cr1 * f4 - sr1 * f5);
+        double d5 = h * ((sr1 * f4 + cr1 * f5) / cp1);
+        if (c == 3) {
+          d3 += 1.0 + h * tp1 * wr1;
+          d4 += -h * wyz1;
+          d5 += h * wr1 / cp1;
+        }
+        if (c == 4) {
+          d3 += h * wyz1 / (cp1 * cp1);
+          d4 += 1.0;
+          d5 += h * wyz1 * sp1 / (cp1 * cp1);
+        }
+        if (c == 5) d5 += 1.0;
         const double e3 = s.v2s[c], e4 = s.v2s[48 + c], e5 = s.v2s[96 + c];
         const double q3 = (1.0 + h * tp * wr) * d3 + (h * wyz / (cp * cp)) * d4 + h * (e3 + tp * (sr * e4 + cr * e5));
         const double q4 = (-h * wyz) * d3 + d4 + h * (cr * e4 - sr * e5);
