@@ -634,6 +634,9 @@ int ddp_begin_solve(ddp_solver_t* s) {
   CK(cudaMemsetAsync(s->d.status, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.iters, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.ls_iters, 0, B * 4, s->stream));
+  // per-SM CTA-slot bitmasks of the backward sweep: all free between launches; re-zero them in case
+  // an earlier launch was aborted with slots taken (they only steer warp roles, never results)
+  CK(cudaMemsetAsync(s->d.sm_slots, 0, 1024 * sizeof(int), s->stream));
   CK(cudaStreamSynchronize(s->stream));
   return 0;
 }
