@@ -4,22 +4,26 @@
 // per trajectory, sequential over t = N-2 .. 0.  Per step the dense contractions run as
 // mma.sync.m8n8k4 f64 (DMMA) tiles out of shared memory; Vxx / Vx never leave the SM.  With
 // S = [fx | fu] (n x (n+m), the two tiles stacked so that 8-wide strips are not padded twice):
-//   A   [W | Wu] = Vxx S
-//   A2  Quu = luu + fu' Wu                             the vector warp inverts it (ilqr.py:655)
-//                                                      while the DMMA warps run B
+//   A1  [W(:, tail) | Wu] = Vxx S(:, strips that contain fu)   first, so that ...
+//   A2  Quu = luu + fu' Wu                                   ... Quu exists early: the vector warp
+//                                                            inverts it (ilqr.py:655) under A3 and B
+//   A3  W(:, head) = Vxx fx(:, the other strips)
 //   B   [Qxx Qx ; Qux Qu] = [lxx lx ; 0 lu] + S' [W | Vx]     Vx rides along as column n of W, so
-//                                                      Qx and Qu cost no extra DMMA; Qxx overwrites Vxx
-//   C1  K = Quu^-1 Qux      C2  Vxx <- Qxx - Qux' K     vector warp: kappa, dV, Vx
+//                                                            Qx and Qu cost no extra DMMA; Qxx overwrites Vxx
+//   C1  K = Quu^-1 Qux      C2  Vxx <- Qxx - Qux' K           vector warp: kappa, dV, Vx
 // The fx / x_bar / u_bar tiles of step t-1 are prefetched into the other half of a double
 // buffer by 1-D bulk TMA (cp.async.bulk + mbarrier) while step t computes, fu is refilled as
 // soon as it is dead; when the tile sizes are not 16-byte multiples (odd n) the same schedule
 // runs on 8-byte cp.async copies issued by all threads.
 // Warp roles (warp id % 4 selects the SM sub-partition, and DMMA and DFMA share the fp64 pipe of
-// their sub-partition): warps 0-2 are DMMA warps, each owning a third of the column strips (or
-// row tiles) of every product, so an operand fragment loaded from shared memory feeds 2-6
-// DMMAs; warp 3 does the serial fp64 work (cost gradients, the inverse of Quu, kappa, dV, Vx)
-// on the fourth sub-partition, where its dependent DFMA chains do not queue behind DMMAs: that
-// chain is the latency-critical path of a step.
+// their sub-partition): a CTA is 4 warps, three DMMA warps that each own a third of the row
+// tiles (or column strips) of every product, so an operand fragment fetched from shared memory
+// feeds 2-6 DMMAs, and one vector warp for the serial fp64 work (cost gradients, the inverse of
+// Quu -- Newton-Schulz on the tensor pipe seeded with the previous step's inverse, Gauss-Jordan
+// as fallback --, kappa, dV, Vx).  The vector role goes to warp `slot`, the CTA's residency slot
+// on its SM (per-SM bitmask in global memory), so the four CTAs of an SM put their vector warps
+// on four different sub-partitions and every sub-partition hosts three DMMA warps.
+// DESIGN.md section 3 has the measured phase times and what was tried without gain.
 #pragma once
 #include "kernels.cuh"
 
