@@ -265,14 +265,14 @@ def run_b200(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
-    e0.record()
+    e0.record(solver._stream)
     for _ in range(K):
         solver.iterate()
         gather_costs()
         ms = solver.timings_ms()          # device events recorded inside the library, no extra sync
         for k in phase_ms:
             phase_ms[k] += ms[k]
-    e1.record()
+    e1.record(solver._stream)
     barrier()
     t_host1 = time.perf_counter()
     elapsed_ms = e0.elapsed_time(e1)
@@ -315,10 +315,10 @@ def run_b200(args):
     it0e = solver.get_int(_lib.I_ITERS).astype(np.int64)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
+    f0.record(solver._stream)
     for _ in range(K):
         e2e_step()
-    f1.record()
+    f1.record(solver._stream)
     barrier()
     e2e_ms = f0.elapsed_time(f1)
     units_e2e_local = int((solver.get_int(_lib.I_ITERS).astype(np.int64) - it0e).sum())

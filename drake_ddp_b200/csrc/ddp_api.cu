@@ -13,7 +13,6 @@
 #include "../../include/ddp_b200.h"
 #include "kernels.cuh"
 #include "backward_mma.cuh"
-#include "quadruped_linearize.cuh"
 #include "quadruped_fused.cuh"
 #include "quadruped_rollout.cuh"
 
@@ -31,8 +30,12 @@ static thread_local std::string g_err;
 
 struct ddp_solver {
   int model, np;
+  int device;            // ordinal of the GPU the arena lives on; every entry point runs under it
   Dev d;
   cudaStream_t stream;
+  // per-solver (hence per-device) launch configuration, set on first use
+  bool cfg_bwd_mma, cfg_bwd;
+  int fused_ctas;
   std::vector<double> eps_host;
   double beta;
   int* h_counters;  // pinned [2]
@@ -41,19 +44,30 @@ struct ddp_solver {
   long long launches;
   bool timings_valid;
   bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
-  bool quad_structured;  // opt-in (DDP_QUAD_STRUCTURED=1): two-kernel structured quadruped linearization
   bool quad_rollout8;    // 8-lane quadruped rollout (DDP_QUAD_ROLLOUT=generic selects rollout_kernel)
   bool quad_fused;       // fused structured quadruped linearization (DDP_QUAD_LINEARIZE=fused|ad)
-  double* quadG;         // quadruped fast path: local leg Jacobians [B*T][sub][4][144]
-  double* quadXmid;      //                      state after each substep [B*T][sub][36]
-  int quad_sub;          // substeps of the quadruped model (0: fast path unavailable)
-  unsigned long long* quadTab;  // gather descriptors of the substep Jacobian assembly
+  int quad_sub;          // substeps of the quadruped model (the fused linearization needs 2)
   // array table
   double* darr[16];
   size_t dsize[16];
 };
 
 namespace {
+
+// Every entry point that takes a solver runs with the solver's device current and restores the
+// caller's device on return: the arena, the stream and the cudaFuncSetAttribute opt-ins are all
+// per device, and the caller may have another GPU current.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define GUARD(s) DeviceGuard guard_((s)->device)
 
 struct Carver {
   char* base;
@@ -69,8 +83,7 @@ struct Carver {
 
 constexpr int kMaxEps = 2048;
 
-void carve(Dev& d, double** params, int np, Carver& c, int model, double** quadG, double** quadXmid,
-           unsigned long long** quadTab) {
+void carve(Dev& d, double** params, int np, Carver& c) {
   const size_t B = d.B, N = d.N, T = d.T, n = d.n, m = d.m, A = d.A;
   *params = c.take<double>(np);
   d.Q = c.take<double>(n * n);
@@ -100,6 +113,8 @@ void carve(Dev& d, double** params, int np, Carver& c, int model, double** quadG
   d.resolved = c.take<int>(B);
   d.acc = c.take<int>(B);
   d.iters = c.take<int>(B);
+  d.active_save = c.take<int>(B);
+  d.status_save = c.take<int>(B);
   d.counters = c.take<int>(4);
   d.sm_slots = c.take<int>(1024);
   d.unres = c.take<int>(B);
@@ -115,14 +130,6 @@ void carve(Dev& d, double** params, int np, Carver& c, int model, double** quadG
   d.nseg[1] = c.take<int>(B);
   d.evallist = c.take<int>(B * T);
   d.evalcount = c.take<int>(B);
-  *quadG = nullptr;
-  *quadXmid = nullptr;
-  *quadTab = nullptr;
-  if (model == MODEL_QUADRUPED && getenv("DDP_QUAD_STRUCTURED")) {  // opt-in path only
-    *quadG = c.take<double>(((B * T + 7) / 8) * 2 * 144 * 32);
-    *quadXmid = c.take<double>(B * T * 2 * 36);
-    *quadTab = c.take<unsigned long long>(kQuadTabSize);
-  }
 }
 
 int model_dims(int model_id, int* n, int* m, int* np) {
@@ -153,15 +160,14 @@ template <class Model>
 int launch_backward_mma(ddp_solver* s) {
   typedef BwdMmaCfg<Model::n, Model::m> C;
   const size_t smem = sizeof(BwdMmaSmem<Model::n, Model::m>);
-  static bool configured = false;
-  if (!configured) {
+  if (!s->cfg_bwd_mma) {
     cudaError_t e = cudaFuncSetAttribute(backward_mma_kernel<Model>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       g_err = std::string("cudaFuncSetAttribute(backward_mma): ") + cudaGetErrorString(e);
       return DDP_ERR_CUDA;
     }
-    configured = true;
+    s->cfg_bwd_mma = true;
   }
   backward_mma_kernel<Model><<<s->d.B, C::NT, smem, s->stream>>>(s->d);
   s->launches++;
@@ -174,15 +180,14 @@ int launch_backward(ddp_solver* s) {
   }
   constexpr int NT = Cfg<Model>::BWD_THREADS;
   const size_t smem = sizeof(BwdSmem<Model::n, Model::m>);
-  static bool configured = false;
-  if (!configured) {
+  if (!s->cfg_bwd) {
     cudaError_t e = cudaFuncSetAttribute(backward_kernel<Model, NT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       g_err = std::string("cudaFuncSetAttribute(backward): ") + cudaGetErrorString(e);
       return DDP_ERR_CUDA;
     }
-    configured = true;
+    s->cfg_bwd = true;
   }
   backward_kernel<Model, NT><<<s->d.B, NT, smem, s->stream>>>(s->d);
   s->launches++;
@@ -202,41 +207,27 @@ int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
   DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base, per_traj, n_items));
   return 0;
 }
-int launch_quad_linearize(ddp_solver* s, const int* list, const int* count) {
-  const size_t items = (size_t)s->d.B * s->d.T;
-  quad_legjac_kernel<<<cdiv(items * 4, 128), 128, 0, s->stream>>>(s->d, list, count, s->quadG, s->quadXmid,
-                                                                    s->quad_sub);
-  s->launches++;
-  quad_chain_kernel<<<(unsigned)items, kQuadThreads, 0, s->stream>>>(s->d, list, count, s->quadG, s->quadXmid,
-                                                                      s->quadTab, s->quad_sub);
-  s->launches++;
-  return 0;
-}
 int launch_quad_fused(ddp_solver* s, const int* list, const int* count) {
   const size_t smem = sizeof(QfWarpSmem) * kQfWarps;
-  static int ctas = 0;
-  if (!ctas) {
+  if (!s->fused_ctas) {
     cudaError_t e = cudaFuncSetAttribute(quad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       g_err = std::string("cudaFuncSetAttribute(quad_fused): ") + cudaGetErrorString(e);
       return DDP_ERR_CUDA;
     }
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quad_fused_kernel, kQfWarps * 32, smem);
-    ctas = sms * (per_sm > 0 ? per_sm : 1);
+    s->fused_ctas = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int n_items = s->d.B * s->d.T;
-  const int grid = std::min(ctas, cdiv(n_items, kQfWarps));
+  const int grid = std::min(s->fused_ctas, cdiv(n_items, kQfWarps));
   quad_fused_kernel<<<grid, kQfWarps * 32, smem, s->stream>>>(s->d, list, count, n_items);
   s->launches++;
   return 0;
 }
 int do_linearize(ddp_solver* s, const int* list, const int* count) {
   if (s->model == MODEL_QUADRUPED && s->quad_sub == 2 && s->quad_fused) return launch_quad_fused(s, list, count);
-  if (s->model == MODEL_QUADRUPED && s->quad_sub > 0 && s->quad_structured && s->quadG)
-    return launch_quad_linearize(s, list, count);
   DDP_MODEL_SWITCH(s->model, return launch_linearize<Model>(s, list, count));
   return 0;
 }
@@ -265,7 +256,7 @@ int phase_linesearch(ddp_solver* s, bool sync_rounds) {
     pick_kernel<<<cdiv(n_traj, 128), 128, 0, s->stream>>>(d, ls_base, per_traj, n_traj);
     s->launches++;
     {
-      dim3 grid(cdiv((size_t)d.N * d.n + (size_t)d.T * d.m, 256 * 4), d.B);
+      dim3 grid(d.B, cdiv((size_t)d.N * d.n + (size_t)d.T * d.m, 256 * 4));
       commit_kernel<<<grid, 256, 0, s->stream>>>(d);
       s->launches++;
     }
@@ -292,8 +283,7 @@ int phase_derivatives(ddp_solver* s) {
     LAUNCH1(kp_set_interval_kernel, d);
   } else if (d.kp_method == DDP_KP_ADAPTIVE_JERK) {
     if (d.N > 3) {
-      dim3 grid(cdiv(d.N - 3, 128), d.B);
-      jerk_flag_kernel<<<grid, 128, 0, s->stream>>>(d);
+      jerk_flag_kernel<<<cdiv((size_t)d.B * (d.N - 3), 128), 128, 0, s->stream>>>(d);
       s->launches++;
     }
     LAUNCH1(jerk_scan_kernel, d);
@@ -321,8 +311,7 @@ int phase_derivatives(ddp_solver* s) {
   }
   if (!(d.kp_method == DDP_KP_SET_INTERVAL && d.minN == 1)) {
     LAUNCH1(segments_kernel, d);
-    dim3 grid(d.T, d.B);
-    interp_kernel<<<grid, 128, 0, s->stream>>>(d);
+    interp_kernel<<<(unsigned)((size_t)d.B * d.T), 128, 0, s->stream>>>(d);
     s->launches++;
   }
   return 0;
@@ -421,9 +410,8 @@ size_t ddp_workspace_bytes(int model_id, int N, int B, int A) {
   d.B = B;
   d.A = A;
   Carver c{nullptr, 0};
-  double *p, *g1, *g2;
-  unsigned long long* g3;
-  carve(d, &p, np, c, model_id, &g1, &g2, &g3);
+  double* p;
+  carve(d, &p, np, c);
   return c.off + 256;
 }
 
@@ -434,6 +422,7 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
     g_err = "unknown model id";
     return DDP_ERR_ARG;
   }
+  *out = nullptr;
   if (nparams != np || N < 3 || B < 1 || A < 1 || !workspace_dev || !params_host) {
     g_err = "bad argument (nparams/N/B/A/workspace)";
     return DDP_ERR_ARG;
@@ -442,25 +431,36 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
     g_err = "workspace too small";
     return DDP_ERR_WORKSPACE;
   }
+  // the arena decides the device: every later call switches to it (and back)
+  cudaPointerAttributes attr;
+  CK(cudaPointerGetAttributes(&attr, workspace_dev));
+  if (attr.type != cudaMemoryTypeDevice) {
+    g_err = "workspace_dev is not device memory";
+    return DDP_ERR_ARG;
+  }
   ddp_solver* s = new ddp_solver();
   memset(&s->d, 0, sizeof(Dev));
+  s->device = attr.device;
   s->model = model_id;
   s->np = np;
   s->stream = (cudaStream_t)stream;
   s->launches = 0;
   s->timings_valid = false;
+  s->cfg_bwd_mma = s->cfg_bwd = false;
+  s->fused_ctas = 0;
+  s->h_counters = nullptr;
+  for (int i = 0; i < 4; ++i) s->ev[i] = nullptr;
   s->scalar_backward = getenv("DDP_SCALAR_BACKWARD") != nullptr;
   Dev& d = s->d;
   d.n = n; d.m = m; d.N = N; d.T = N - 1; d.B = B; d.A = A;
   Carver c{(char*)workspace_dev, 0};
   double* params;
-  carve(d, &params, np, c, model_id, &s->quadG, &s->quadXmid, &s->quadTab);
+  carve(d, &params, np, c);
   s->quad_sub = 0;
   if (model_id == MODEL_QUADRUPED) {
     const int sub = (int)params_host[1];
     if (sub == 1 || sub == 2) s->quad_sub = sub;
   }
-  s->quad_structured = getenv("DDP_QUAD_STRUCTURED") != nullptr;
   {
     const char* inv = getenv("DDP_BWD_INVERSE");   // "gauss-jordan": no Newton-Schulz (debug / parity tests)
     s->d.bwd_flags = (inv && std::string(inv) == "gauss-jordan") ? 1 : 0;
@@ -468,45 +468,58 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
     s->quad_rollout8 = !(rmode && std::string(rmode) == "generic");
     // default: the fused structured kernel; DDP_QUAD_LINEARIZE=ad selects the generic AD kernel
     const char* mode = getenv("DDP_QUAD_LINEARIZE");
-    s->quad_fused = !s->quad_structured && !(mode && std::string(mode) == "ad");
+    s->quad_fused = !(mode && std::string(mode) == "ad");
   }
   d.params = params;
-  CK(cudaMemsetAsync(workspace_dev, 0, c.off, s->stream));
-  CK(cudaMemcpyAsync(params, params_host, np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  if (s->quadTab) {
-    static unsigned long long tab[kQuadTabSize];
-    quad_build_table(tab);
-    CK(cudaMemcpyAsync(s->quadTab, tab, sizeof(tab), cudaMemcpyHostToDevice, s->stream));
+  GUARD(s);
+  // from here on a failure must release what was acquired: run the rest in a lambda and
+  // destroy the half-built solver if it reports an error
+  auto init = [&]() -> int {
+    CK(cudaMemsetAsync(workspace_dev, 0, c.off, s->stream));
+    CK(cudaMemcpyAsync(params, params_host, np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaHostAlloc(&s->h_counters, 4 * sizeof(int), cudaHostAllocDefault));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&s->ev[i]));
+    // Q = R = Qf = I (ilqr.py:65-67)
+    std::vector<double> I(n * n, 0.0), Im(m * m, 0.0);
+    for (int i = 0; i < n; ++i) I[i * n + i] = 1.0;
+    for (int i = 0; i < m; ++i) Im[i * m + i] = 1.0;
+    CK(cudaMemcpyAsync((void*)d.Q, I.data(), n * n * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync((void*)d.Qf, I.data(), n * n * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync((void*)d.R, Im.data(), m * m * 8, cudaMemcpyHostToDevice, s->stream));
+    d.diag_cost = 1;
+    CK(cudaStreamSynchronize(s->stream));
+    int rc = ddp_set_options(s, 1e-2, 0.95, 0.0);
+    if (rc) return rc;
+    rc = ddp_set_keypoints(s, DDP_KP_SET_INTERVAL, 1, 0, 0.0, 0.0);
+    if (rc) return rc;
+    return ddp_begin_solve(s);
+  };
+  const int rc = init();
+  if (rc) {
+    const std::string keep = g_err;
+    ddp_destroy(s);
+    g_err = keep;
+    return rc;
   }
-  CK(cudaHostAlloc(&s->h_counters, 4 * sizeof(int), cudaHostAllocDefault));
-  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&s->ev[i]));
-  // Q = R = Qf = I (ilqr.py:65-67)
-  std::vector<double> I(n * n, 0.0), Im(m * m, 0.0);
-  for (int i = 0; i < n; ++i) I[i * n + i] = 1.0;
-  for (int i = 0; i < m; ++i) Im[i * m + i] = 1.0;
-  CK(cudaMemcpyAsync((void*)d.Q, I.data(), n * n * 8, cudaMemcpyHostToDevice, s->stream));
-  CK(cudaMemcpyAsync((void*)d.Qf, I.data(), n * n * 8, cudaMemcpyHostToDevice, s->stream));
-  CK(cudaMemcpyAsync((void*)d.R, Im.data(), m * m * 8, cudaMemcpyHostToDevice, s->stream));
-  d.diag_cost = 1;
-  CK(cudaStreamSynchronize(s->stream));
   *out = s;
-  int rc = ddp_set_options(s, 1e-2, 0.95, 0.0);
-  if (rc) return rc;
-  rc = ddp_set_keypoints(s, DDP_KP_SET_INTERVAL, 1, 0, 0.0, 0.0);
-  if (rc) return rc;
-  return ddp_begin_solve(s);
+  return 0;
 }
 
 int ddp_destroy(ddp_solver_t* s) {
   if (!s) return 0;
-  cudaStreamSynchronize(s->stream);
-  for (int i = 0; i < 4; ++i) cudaEventDestroy(s->ev[i]);
-  cudaFreeHost(s->h_counters);
+  {
+    GUARD(s);
+    cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < 4; ++i)
+      if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+  }
   delete s;
   return 0;
 }
 
 int ddp_set_options(ddp_solver_t* s, double delta, double beta, double gamma) {
+  GUARD(s);
   if (!(beta > 0.0 && beta < 1.0)) {
     g_err = "beta must be in (0,1)";
     return DDP_ERR_ARG;
@@ -555,6 +568,7 @@ int ddp_set_keypoints(ddp_solver_t* s, int method, int minN, int maxN, double je
 }
 
 int ddp_set_cost(ddp_solver_t* s, const double* Q, const double* R, const double* Qf) {
+  GUARD(s);
   const int n = s->d.n, m = s->d.m;
   bool diag = true;
   for (int i = 0; i < n && diag; ++i)
@@ -578,6 +592,7 @@ int ddp_set_cost(ddp_solver_t* s, const double* Q, const double* R, const double
 }
 
 int ddp_set_target(ddp_solver_t* s, const double* x_nom, int per_trajectory) {
+  GUARD(s);
   const int n = s->d.n, B = s->d.B;
   if (per_trajectory) {
     CK(cudaMemcpyAsync((void*)s->d.x_nom, x_nom, (size_t)B * n * 8, cudaMemcpyHostToDevice, s->stream));
@@ -585,19 +600,22 @@ int ddp_set_target(ddp_solver_t* s, const double* x_nom, int per_trajectory) {
     std::vector<double> rep((size_t)B * n);
     for (int b = 0; b < B; ++b) memcpy(&rep[(size_t)b * n], x_nom, n * 8);
     CK(cudaMemcpyAsync((void*)s->d.x_nom, rep.data(), (size_t)B * n * 8, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaStreamSynchronize(s->stream));   // rep goes out of scope
+    return 0;
   }
   CK(cudaStreamSynchronize(s->stream));
   return 0;
 }
 
 int ddp_set_initial_state(ddp_solver_t* s, const double* x0) {
+  GUARD(s);
   CK(cudaMemcpyAsync((void*)s->d.x0, x0, (size_t)s->d.B * s->d.n * 8, cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   return 0;
 }
 
 int ddp_set_initial_guess(ddp_solver_t* s, const double* u_guess) {
+  GUARD(s);
   CK(cudaMemcpyAsync(s->d.u_bar, u_guess, (size_t)s->d.B * s->d.T * s->d.m * 8, cudaMemcpyHostToDevice,
                      s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -605,6 +623,7 @@ int ddp_set_initial_guess(ddp_solver_t* s, const double* u_guess) {
 }
 
 int ddp_reset(ddp_solver_t* s) {
+  GUARD(s);
   const int which[] = {DDP_X_BAR, DDP_U_BAR, DDP_K, DDP_KAPPA, DDP_DV, DDP_FX, DDP_FU};
   for (int w : which) {
     ArrInfo a = arr(s, w);
@@ -614,6 +633,7 @@ int ddp_reset(ddp_solver_t* s) {
 }
 
 int ddp_mpc_shift(ddp_solver_t* s, int replan_steps) {
+  GUARD(s);
   if (replan_steps < 1 || replan_steps >= s->d.N) {
     g_err = "replan_steps must be in [1, N)";
     return DDP_ERR_ARG;
@@ -625,6 +645,7 @@ int ddp_mpc_shift(ddp_solver_t* s, int replan_steps) {
 }
 
 int ddp_begin_solve(ddp_solver_t* s) {
+  GUARD(s);
   const int B = s->d.B;
   std::vector<double> inf(B, INFINITY);
   std::vector<int> ones(B, 1);
@@ -642,6 +663,7 @@ int ddp_begin_solve(ddp_solver_t* s) {
 }
 
 int ddp_iterate(ddp_solver_t* s, int* n_active) {
+  GUARD(s);
   int rc = iterate_impl(s, true, false);
   if (rc) return rc;
   CK(cudaMemcpyAsync(s->h_counters + 1, s->d.counters + 1, sizeof(int), cudaMemcpyDeviceToHost,
@@ -653,6 +675,7 @@ int ddp_iterate(ddp_solver_t* s, int* n_active) {
 }
 
 int ddp_iterate_linesearch(ddp_solver_t* s) {
+  GUARD(s);
   int rc = iterate_linesearch_impl(s, true, false);
   if (rc) return rc;
   CK(cudaStreamSynchronize(s->stream));
@@ -661,6 +684,7 @@ int ddp_iterate_linesearch(ddp_solver_t* s) {
 }
 
 int ddp_iterate_finish_async(ddp_solver_t* s) {
+  GUARD(s);
   int rc = iterate_finish_impl(s);
   if (rc) return rc;
   CK(cudaMemcpyAsync(s->h_counters + 1, s->d.counters + 1, sizeof(int), cudaMemcpyDeviceToHost,
@@ -669,6 +693,7 @@ int ddp_iterate_finish_async(ddp_solver_t* s) {
 }
 
 int ddp_iterate_wait(ddp_solver_t* s, int* n_active) {
+  GUARD(s);
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
   if (n_active) *n_active = s->h_counters[1];
@@ -676,6 +701,7 @@ int ddp_iterate_wait(ddp_solver_t* s, int* n_active) {
 }
 
 int ddp_solve(ddp_solver_t* s, int max_iters, int* iters_done) {
+  GUARD(s);
   int rc = ddp_begin_solve(s);
   if (rc) return rc;
   int it = 0, n_active = 1;
@@ -689,22 +715,33 @@ int ddp_solve(ddp_solver_t* s, int max_iters, int* iters_done) {
 }
 
 int ddp_run_phase(ddp_solver_t* s, int phase) {
+  GUARD(s);
   Dev& d = s->d;
+  if (phase < DDP_PHASE_LINESEARCH || phase > DDP_PHASE_BACKWARD) {
+    g_err = "unknown phase";
+    return DDP_ERR_ARG;
+  }
+  // every trajectory runs the phase, converged or not; the active flags and statuses of a solve
+  // in progress are put back afterwards
+  CK(cudaMemcpyAsync(d.active_save, d.active, d.B * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+  CK(cudaMemcpyAsync(d.status_save, d.status, d.B * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
   LAUNCH1(begin_iter_kernel, d, 1);
   int rc = 0;
   switch (phase) {
     case DDP_PHASE_LINESEARCH: rc = phase_linesearch(s, true); break;
     case DDP_PHASE_DERIVATIVES: rc = phase_derivatives(s); break;
-    case DDP_PHASE_BACKWARD: rc = do_backward(s); break;
-    default: g_err = "unknown phase"; return DDP_ERR_ARG;
+    default: rc = do_backward(s); break;
   }
   if (rc) return rc;
+  CK(cudaMemcpyAsync(d.active, d.active_save, d.B * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+  CK(cudaMemcpyAsync(d.status, d.status_save, d.B * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
   return 0;
 }
 
 int ddp_get(ddp_solver_t* s, int which, double* dst_host) {
+  GUARD(s);
   ArrInfo a = arr(s, which);
   if (!a.ptr) {
     g_err = "unknown array";
@@ -716,6 +753,7 @@ int ddp_get(ddp_solver_t* s, int which, double* dst_host) {
 }
 
 int ddp_put(ddp_solver_t* s, int which, const double* src_host) {
+  GUARD(s);
   ArrInfo a = arr(s, which);
   if (!a.ptr) {
     g_err = "unknown array";
@@ -727,6 +765,7 @@ int ddp_put(ddp_solver_t* s, int which, const double* src_host) {
 }
 
 int ddp_get_int(ddp_solver_t* s, int which, int* dst_host) {
+  GUARD(s);
   ArrInfo a = iarr(s, which);
   if (!a.ptr) {
     g_err = "unknown int array";
@@ -741,6 +780,7 @@ void* ddp_device_ptr(ddp_solver_t* s, int which) { return arr(s, which).ptr; }
 size_t ddp_array_elems(ddp_solver_t* s, int which) { return arr(s, which).elems; }
 
 int ddp_last_timings(ddp_solver_t* s, float ms[4]) {
+  GUARD(s);
   if (!s->timings_valid) {
     g_err = "no iteration has run";
     return DDP_ERR_ARG;

@@ -24,6 +24,7 @@ struct Dev {
   double *xc, *uc, *Lc, *Ec;
   double *L, *L_new, *eps, *improvement;
   int *ls_iters, *status, *active, *resolved, *acc, *iters, *counters, *unres;
+  int *active_save, *status_save;  // ddp_run_phase (teacher-forced tests) puts these back
   int bwd_flags;  // bit 0: backward_mma_kernel inverts Quu by Gauss-Jordan at every step (no Newton-Schulz)
   int* sm_slots;  // per-SM bitmask of the CTA slots in use (backward_mma_kernel deals warp roles by slot)
   // keypoints
@@ -272,7 +273,7 @@ __global__ void unresolved_kernel(Dev d) {
 
 // u_bar <- u, x_bar <- x of the accepted candidate (ilqr.py:375-376).
 __global__ void commit_kernel(Dev d) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;
   if (!d.active[b]) return;
   const int slot = d.acc[b];
   if (slot < 0) return;
@@ -281,7 +282,7 @@ __global__ void commit_kernel(Dev d) {
   const double* us = d.uc + (size_t)slot * nu;
   double* xd = d.x_bar + (size_t)b * nx;
   double* ud = d.u_bar + (size_t)b * nu;
-  for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nx + nu; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = blockIdx.y * blockDim.x + threadIdx.x; i < nx + nu; i += (size_t)gridDim.y * blockDim.x) {
     if (i < nx) xd[i] = xs[i];
     else ud[i - nx] = us[i - nx];
   }
@@ -354,9 +355,10 @@ __global__ void kp_set_interval_kernel(Dev d) {
 }
 // calc_jerk_profile + threshold test, ilqr.py:470-486,454-455: flag[b][t] = any_i jerk[t,i] > thr
 __global__ void jerk_flag_kernel(Dev d) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (t >= d.N - 3 || !d.active[b]) return;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)d.B * (d.N - 3)) return;
+  const int b = (int)(gid / (d.N - 3)), t = (int)(gid % (d.N - 3));
+  if (!d.active[b]) return;
   const int n = d.n, dof = n / 2;
   const double* x = d.x_bar + ((size_t)b * d.N + t) * n + dof;
   bool any = false;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(128, (Model::n > 8 ? DDP_LIN_MINB : 1)) linear
 // K5  interpolate_derivatives (ilqr.py:596-621): fx_j = fx_s + (fx_e - fx_s)*(j-s)/(e-s)
 // =============================================================================================
 __global__ void interp_kernel(Dev d) {
-  const int t = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.x / d.T, t = blockIdx.x % d.T;
   if (!d.active[b]) return;
   const int s = d.seg_s[(size_t)b * d.T + t];
   if (s < 0 || s == t) return;

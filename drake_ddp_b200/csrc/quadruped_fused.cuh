@@ -20,7 +20,6 @@
 // settings use the generic kernel.
 #pragma once
 #include "backward_mma.cuh"
-#include "quadruped_jac.h"
 
 namespace ddp {
 
@@ -33,6 +32,16 @@ constexpr int kQfWarps = QF_WARPS;   // warps (points in flight) per CTA
 #ifndef QF_MINB
 #define QF_MINB 2
 #endif
+
+// local input j (0..15) of leg l -> global column of [fx | fu] (0..47): base height, roll / pitch /
+// yaw, base twist, the leg's three joint angles, its three joint rates
+__host__ __device__ inline int qf_gcol(int l, int j) {
+  if (j == 0) return 2;
+  if (j < 4) return 2 + j;
+  if (j < 10) return 18 + (j - 4);
+  if (j < 13) return 6 + 3 * l + (j - 10);
+  return 24 + 3 * l + (j - 13);
+}
 
 struct QfWarpSmem {
   double D1v[20 * kQfLd];     // velocity rows of the substep-1 Jacobian d v1/d(q, v, u), 18 x 48 (+2 pad rows)
@@ -65,7 +74,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   // lane -> (leg, pair of local directions) and the global columns of the two directions
   const int leg = lane >> 3, dp = lane & 7;
   const int j0 = 2 * dp, j1 = j0 + 1;
-  const int gc[2] = {QuadJac::gcol(leg, j0), QuadJac::gcol(leg, j1)};
+  const int gc[2] = {qf_gcol(leg, j0), qf_gcol(leg, j1)};
   const bool shared_dir = dp < 5;   // base directions: every leg contributes to the base rows
   const double sx = (leg < 2) ? 1.0 : -1.0, sd = (leg & 1) ? 1.0 : -1.0;
 
@@ -345,7 +354,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       const double sr = trig[1][0], cr = trig[1][1], sp = trig[1][2], cp = trig[1][3];
       const double tp = sp / cp, wy = s.st[2][22], wz = s.st[2][23];
       const double wyz = sr * wy + cr * wz, wr = cr * wy - sr * wz;
-      // D1q rows 3..5 = E1 + h N1 D1v with the Euler-rate matrices of substep 1 (QuadJac::dq_elem)
+      // D1q rows 3..5 = E1 + h N1 D1v with the Euler-rate matrices of substep 1 
       const double sr1 = trig[0][0], cr1 = trig[0][1], sp1 = trig[0][2], cp1 = trig[0][3];
       const double tp1 = sp1 / cp1, wy1 = s.st[1][22], wz1 = s.st[1][23];
       const double wyz1 = sr1 * wy1 + cr1 * wz1, wr1 = cr1 * wy1 - sr1 * wz1;

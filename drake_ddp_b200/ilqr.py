@@ -23,22 +23,98 @@ def _ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
 
-def _as_system(system):
-    """Accept a native AnalyticSystem (has model_id/params).  A Drake System cannot be
-    evaluated in-kernel; point the user at drake_ddp_b200.systems."""
+def _drake_names(system):
+    """Lower-cased names a Drake System / MultibodyPlant / Diagram offers for model matching."""
+    names = []
+    plant = system
+    try:
+        plant = system.GetSubsystemByName("plant")      # Diagram with a plant (cart_pole_with_wall.py:135)
+    except Exception:
+        pass
+    for obj in (system, plant):
+        for getter in ("get_name", "GetSystemName"):
+            try:
+                names.append(str(getattr(obj, getter)()))
+            except Exception:
+                pass
+    try:                                                # MultibodyPlant: model instance names
+        for i in range(plant.num_model_instances()):
+            try:
+                from pydrake.multibody.tree import ModelInstanceIndex
+                names.append(str(plant.GetModelInstanceName(ModelInstanceIndex(i))))
+            except Exception:
+                break
+    except Exception:
+        pass
+    n_geom = 0
+    try:
+        n_geom = int(plant.num_collision_geometries())
+    except Exception:
+        pass
+    return [nm.lower() for nm in names], n_geom
+
+
+def _as_system(system, input_port_index=0):
+    """The ``system`` argument of the reference constructor (/root/reference/ilqr.py:21-58).
+
+    Accepts (i) a native ``AnalyticSystem`` (has model_id/params) and (ii) a discrete-time Drake
+    ``System`` -- a bare ``MultibodyPlant`` plus actuation port index (pendulum.py:74-86) or a
+    ``Diagram`` with an exported input (cart_pole_with_wall.py:135-148).  A Drake object is only
+    *read*, through the same calls the reference makes on it: ``IsDifferenceEquationSystem()``
+    (:37), ``CreateDefaultContext().get_discrete_state_vector().size()`` (:57),
+    ``get_input_port(i).size()`` (:58) and ``time_step()`` (:725); (n, m, dt, names) select the
+    matching fixed analytic model of ``drake_ddp_b200.systems``, which is what the kernels
+    evaluate.  Raises when no analytic model matches."""
     if hasattr(system, "model_id") and hasattr(system, "params"):
         return system
+    if not (hasattr(system, "IsDifferenceEquationSystem") and hasattr(system, "CreateDefaultContext")):
+        raise TypeError(
+            "system must be a drake_ddp_b200.systems.AnalyticSystem or a discrete-time Drake System "
+            "(IsDifferenceEquationSystem / CreateDefaultContext / get_input_port)")
+    from . import systems
+    res = system.IsDifferenceEquationSystem()
+    is_discrete = res[0] if isinstance(res, (tuple, list)) else res
+    assert is_discrete, "must be a discrete-time system"                       # ilqr.py:37
+    n = int(system.CreateDefaultContext().get_discrete_state_vector().size())   # ilqr.py:57
+    m = int(system.get_input_port(input_port_index).size())                     # ilqr.py:58
+    dt = None
+    for get in (lambda: system.time_step(), lambda: system.GetSubsystemByName("plant").time_step(),
+                lambda: res[1]):
+        try:
+            dt = float(get())
+            if dt > 0:
+                break
+        except Exception:
+            continue
+    if not dt or dt <= 0:
+        raise TypeError("cannot read the time step of the Drake system")
+    names, n_geom = _drake_names(system)
+    has = lambda *keys: any(k in nm for nm in names for k in keys)
+    if (n, m) == (2, 1):
+        return systems.pendulum(dt=dt)
+    if (n, m) == (4, 1):
+        if has("acrobot"):
+            return systems.acrobot(dt=dt)
+        if has("wall") or (has("cart") and n_geom > 0):
+            return systems.cart_pole_with_wall(dt=dt)
+        if has("cart"):
+            return systems.cart_pole(dt=dt)
+    if (n, m) == (37, 12):
+        return systems.quadruped_quat(dt=dt)      # mini_cheetah.py:41-52 (quaternion floating base)
+    if (n, m) == (36, 12):
+        return systems.quadruped(dt=dt)
+    if (n, m) == (27, 7):
+        return systems.arm_ball(dt=dt)            # kinova_gen3.py:68 / panda_fr3.py (7 + 7 + 13)
     raise TypeError(
-        "system must be a drake_ddp_b200.systems.AnalyticSystem (fixed analytic model evaluated "
-        "in-kernel); Drake Systems are not evaluated on the GPU path -- build the matching model "
-        "with drake_ddp_b200.systems.<model>()")
+        f"no analytic model for a Drake system with n={n}, m={m}, names={names}: the GPU path "
+        "evaluates fixed analytic models (drake_ddp_b200.systems); pass one explicitly")
 
 
 class BatchedILQR:
     """B independent iLQR problems sharing one model, horizon and cost."""
 
     def __init__(self, system, num_timesteps, batch=1, delta=1e-2, beta=0.95, gamma=0.0,
-                 derivs_keypoint_method=None, ls_parallel=None, device=None):
+                 derivs_keypoint_method=None, ls_parallel=None, device=None, input_port_index=0):
         import torch
 
         L = _lib.lib()  # raises if the CUDA extension is missing
@@ -46,7 +122,7 @@ class BatchedILQR:
             raise RuntimeError("drake_ddp_b200 needs a CUDA device (no CPU fallback)")
         self._torch = torch
         self._L = L
-        self.system = _as_system(system)
+        self.system = _as_system(system, input_port_index)
         self.N, self.B = int(num_timesteps), int(batch)
         self.n, self.m = self.system.n, self.system.m
         self.T = self.N - 1
@@ -73,7 +149,9 @@ class BatchedILQR:
         assert nbytes > 0, "bad (model, N, B, A)"
         with torch.cuda.device(self.device):
             self._arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._stream = torch.cuda.current_stream(self.device)
+            # the solver's own stream on its own device: the library switches to the arena's
+            # device inside every call, so the caller may keep any GPU current
+            self._stream = torch.cuda.Stream(device=self.device)
             h = ctypes.c_void_p()
             _lib.check(L.ddp_create(ctypes.byref(h), self.system.model_id, _ptr(params), params.size,
                                     self.N, self.B, self.A, ctypes.c_void_p(self._arena.data_ptr()),
@@ -320,7 +398,7 @@ class IterativeLinearQuadraticRegulator:
 
     def __init__(self, system, num_timesteps, input_port_index=0, delta=1e-2, beta=0.95, gamma=0.0,
                  derivs_keypoint_method=None, ls_parallel=None):
-        self.system = _as_system(system)
+        self.system = _as_system(system, input_port_index)
         self.N = num_timesteps
         self.delta, self.beta, self.gamma = delta, beta, gamma
         self.n, self.m = self.system.n, self.system.m

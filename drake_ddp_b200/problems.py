@@ -110,10 +110,8 @@ def quadruped_stand(sysm: systems.AnalyticSystem, knee=1.6):
 
 def quadruped(N: int = 200, target_vel: float = 1.0, keypoints=None) -> Problem:
     """mini_cheetah.py:22-69,147-180 re-expressed for the n=36 Euler-angle model
-    (script horizon 50; config C4 uses N=200).  Batch seeds perturb x0 by sigma = 0.002: the
-    feet sink only 1.2 mm into the compliant ground at rest, so centimetre-scale perturbations
-    would lift or bury them and the 0.8 s open-loop first rollout would collapse (see
-    DESIGN.md "Conditioning")."""
+    (script horizon 50; config C4 uses N=200).  Batch seeds perturb x0 by sigma = 0.01
+    (SURVEY 8d)."""
     sysm = systems.quadruped(dt=4e-3)
     dt = sysm.dt
     q0, u_stand = quadruped_stand(sysm)
@@ -130,7 +128,7 @@ def quadruped(N: int = 200, target_vel: float = 1.0, keypoints=None) -> Problem:
     Qf = np.diag(np.hstack([5 * Qq_base, 0.1 + Qq_legs, Qv_base, Qv_legs]))
     u_guess = np.repeat(u_stand[:, None], N - 1, axis=1)
     return Problem("quadruped", sysm, N, x0, x_nom, dt * Q, dt * R, Qf, u_guess, beta=0.5,
-                   delta=1e-2, gamma=0.0, keypoints=keypoints, sigma=0.002,
+                   delta=1e-2, gamma=0.0, keypoints=keypoints, sigma=0.01,
                    extra={"u_stand": u_stand, "target_vel": target_vel})
 
 

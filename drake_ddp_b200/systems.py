@@ -87,8 +87,17 @@ def cart_pole_with_wall(dt=1e-2, mc=10.0, mp=1.0, length=0.5, g=9.81, ball_radiu
 def quadruped(dt=4e-3, substeps=2, mass=8.252, inertia=(0.07, 0.26, 0.242),
               joint_inertia=(0.03, 0.03, 0.03), joint_damping=1.0,
               l_abad=0.062, l_thigh=0.209, l_shank=0.19, hip_x=0.19, hip_y=0.049,
-              foot_radius=0.0175, modulus=5e6, mu=0.6, v_stiction=0.2, g=9.81) -> AnalyticSystem:
-    """mini_cheetah-scale lumped quadruped (masses/lengths from mini_cheetah_mesh.urdf)."""
+              foot_radius=0.0175, modulus=1.75e5, mu=0.6, v_stiction=0.2, g=9.81) -> AnalyticSystem:
+    """mini_cheetah-scale lumped quadruped (masses/lengths from mini_cheetah_mesh.urdf).
+
+    ``modulus`` is the modulus of the model's compliant-sphere/rigid-plane closed form
+    F = pi E' d^2 (1 - 2d/3R).  The script puts RIGID feet (r = 0.0175) on a COMPLIANT ground box of
+    thickness 1 m with hydroelastic modulus E = 5e6 (mini_cheetah.py:75-101): the box's pressure
+    field rises linearly from 0 at the surface to E at the medial plane 0.5 m down, so a foot that
+    sinks d feels F = int (E/0.5)(d - rho^2/2R) 2 pi rho d rho = 2 pi E R d^2.  Matching the d^2
+    term gives E' = 2 E R / (1 m) = 1.75e5, the default here (rest penetration 6 mm).  Used directly as
+    E' the script's 5e6 makes the contact 29x stiffer than the script's own scene and the N=200
+    solve chaotic."""
     p = [dt, float(substeps), mass, *inertia, *joint_inertia, joint_damping, l_abad, l_thigh,
          l_shank, hip_x, hip_y, foot_radius, modulus, mu, v_stiction, g]
     return AnalyticSystem("quadruped", MODEL_QUADRUPED, 36, 12, np.array(p, dtype=np.float64))

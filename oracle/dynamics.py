@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libhostmodels.so")
 _SRC = os.path.join(_HERE, "hostmodels.cpp")
 _HDRS = [os.path.join(_HERE, "..", "drake_ddp_b200", "csrc", h)
-         for h in ("models.h", "dual.h", "quadruped_jac.h", "quadruped_legjac.h")]
+         for h in ("models.h", "dual.h")]
 _lib = None
 
 
@@ -43,7 +43,6 @@ def lib():
         L.hostmodel_dims.argtypes = [ctypes.c_int, ip, ip, ip]
         L.hostmodel_step.argtypes = [ctypes.c_int, dp, dp, dp, dp]
         L.hostmodel_jac.argtypes = [ctypes.c_int, dp, dp, dp, dp, dp, dp]
-        L.hostmodel_quadruped_jac_structured.argtypes = [dp, dp, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -73,15 +72,6 @@ class HostDynamics:
         xn = np.empty(self.n)
         self._L.hostmodel_step(self.model_id, _p(x), _p(u), _p(self.params), _p(xn))
         return xn
-
-    def jac_structured(self, x, u):
-        """Quadruped only: closed-form leg Jacobians + chain rule (csrc/quadruped_jac.h)."""
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        u = np.ascontiguousarray(u, dtype=np.float64)
-        fx = np.empty((self.n, self.n))
-        fu = np.empty((self.n, self.m))
-        self._L.hostmodel_quadruped_jac_structured(_p(x), _p(u), _p(self.params), _p(fx), _p(fu))
-        return fx, fu
 
     def jac(self, x, u):
         x = np.ascontiguousarray(x, dtype=np.float64)

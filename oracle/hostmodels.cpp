@@ -8,7 +8,6 @@
 //
 // Build: g++ -O2 -shared -fPIC oracle/hostmodels.cpp -o oracle/_build/libhostmodels.so
 #include "../drake_ddp_b200/csrc/models.h"
-#include "../drake_ddp_b200/csrc/quadruped_jac.h"
 
 namespace {
 template <class Model>
@@ -46,13 +45,6 @@ int jac_impl(const double* x, const double* u, const double* p, double* xn, doub
 }  // namespace
 
 extern "C" {
-// structured (closed-form legs + chain rule) Jacobian of the quadruped step, to be compared with
-// hostmodel_jac (forward-mode AD) by the tests
-int hostmodel_quadruped_jac_structured(const double* x, const double* u, const double* p, double* fx,
-                                       double* fu) {
-  ddp::QuadJac::step_jac_serial(x, u, p, fx, fu);
-  return 0;
-}
 int hostmodel_dims(int model_id, int* n, int* m, int* np) {
   DDP_MODEL_SWITCH(model_id, { *n = Model::n; *m = Model::m; *np = Model::np; });
   return 0;

@@ -68,8 +68,70 @@ def run_reference(prob, kp, iters):
                 kappa=r.kappa, dV_coeff=r.dV_coeff, fx=r.fx, fu=r.fu)
 
 
+# Full Solve() runs to convergence through the reference's own loop (ilqr.py:669-710), the
+# north-star quantity "final cost of a converged Solve()": name -> (factory, keypoints, seeds of
+# the batch_x0(., seed=0) rows solved).  Stored per trajectory: per-iteration costs / eps /
+# ls_iters (recorded by wrapping the bound _forward_pass, the reference source is untouched),
+# the returned final cost, x_bar, u_bar; K, kappa for the first trajectory only (size).
+SOLVE_CASES = {
+    "solve_quadruped_N200": (lambda: problems.quadruped(200), None, [0, 1, 2, 3, 4, 5, 6, 7]),
+    "solve_quadruped_quat_N200": (lambda: problems.quadruped_quat(200), None, [0, 1, 2, 3]),
+    "solve_arm_ball_N400_setInterval5": (lambda: problems.arm_ball(400), "problem", [0, 1, 2, 3]),
+    "solve_pendulum_N100": (lambda: problems.pendulum(100), None, [0]),
+}
+
+
+def run_reference_solve(prob, kp, x0):
+    ref, ref_utils = load_reference_ilqr()
+    method = None if kp is None else ref_utils.derivs_interpolation(
+        kp.keypoint_method, kp.minN, kp.maxN, kp.jerk_threshold, kp.iterative_error_threshold)
+    r = ref.IterativeLinearQuadraticRegulator(ShimSystem(prob.system), prob.N, delta=prob.delta,
+                                              beta=prob.beta, gamma=prob.gamma,
+                                              derivs_keypoint_method=method)
+    r.SetInitialState(x0.copy())
+    r.SetTargetState(prob.x_nom)
+    r.SetRunningCost(prob.Q, prob.R)
+    r.SetTerminalCost(prob.Qf)
+    r.SetInitialGuess(prob.u_guess.copy())
+    rec = []
+    inner = r._forward_pass
+
+    def recording_forward_pass(L_last):
+        out = inner(L_last)
+        rec.append(out)
+        return out
+
+    r._forward_pass = recording_forward_pass
+    failed = 0
+    with contextlib.redirect_stdout(io.StringIO()):
+        try:
+            x, u, _, L = r.Solve()
+        except RuntimeError:            # "linesearch failed after %s iterations" (ilqr.py:337)
+            failed, L = 1, rec[-1][0] if rec else np.inf
+    return dict(final_cost=L, failed=failed, costs=np.array([o[0] for o in rec]),
+                eps=np.array([o[1] for o in rec]), ls_iters=np.array([o[2] for o in rec]),
+                x_bar=r.x_bar.copy(), u_bar=r.u_bar.copy(), K=r.K.copy(), kappa=r.kappa.copy())
+
+
+def main_solve():
+    for name, (factory, kp, rows) in SOLVE_CASES.items():
+        prob = factory()
+        kpc = prob.keypoints if kp == "problem" else kp
+        x0s = prob.batch_x0(max(rows) + 1, seed=0) if prob.sigma > 0 else np.repeat(prob.x0[None], max(rows) + 1, 0)
+        out = {"rows": np.array(rows)}
+        for i, b in enumerate(rows):
+            g = run_reference_solve(prob, kpc, x0s[b])
+            for k, v in g.items():
+                if k in ("K", "kappa", "x_bar") and i > 0:
+                    continue
+                out[f"{k}_{b}"] = v
+            print(name, b, "final", g["final_cost"], "iters", len(g["costs"]), "failed", g["failed"])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    main_solve()
     for name, (factory, kp, iters) in CASES.items():
         prob = factory()
         out = run_reference(prob, kp, iters)

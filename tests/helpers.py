@@ -43,3 +43,38 @@ def gpu_state(s, b=0):
     g = s.get
     return (g(_lib.X_BAR)[b], g(_lib.U_BAR)[b], g(_lib.K)[b], g(_lib.KAPPA)[b], g(_lib.DV)[b],
             g(_lib.FX)[b], g(_lib.FU)[b])
+
+
+# ---- many oracle solves in parallel (converged-Solve parity tests) ------------------------------
+def _oracle_solve_worker(args):
+    """Solve one problem to convergence with the oracle; x0 scaled by each of ``scales``.
+    Returns per scale: (costs per iteration, failed flag, K, kappa)."""
+    import os
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    expr, x0, scales, want_gains = args
+    from drake_ddp_b200 import problems  # noqa: F401  (used by eval)
+    prob = eval(expr)
+    out = []
+    for sc in scales:
+        o = make_oracle(prob, x0=x0 * sc)
+        failed = False
+        try:
+            o.solve(max_iters=200)
+        except RuntimeError:
+            failed = True
+        out.append(([r.L for r in o.trace], failed, o.K.copy() if want_gains else None,
+                    o.kappa.copy() if want_gains else None))
+    return out
+
+
+def oracle_solve_many(expr, x0s, scales=(1.0,), want_gains=True, procs=None):
+    """``expr`` is a problem factory expression such as "problems.quadruped(200)" (evaluated in
+    the worker processes, which only run the CPU oracle)."""
+    import multiprocessing as mp
+    import os
+    procs = procs or max(1, min(len(x0s), (os.cpu_count() or 2)))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        return pool.map(_oracle_solve_worker, [(expr, x0s[b], tuple(scales), want_gains) for b in range(len(x0s))],
+                        chunksize=1)

@@ -314,12 +314,10 @@ def test_full_size_c4_properties():
         prev = cost
 
 
-def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
-    """The structured quadruped linearizations -- the fused kernel (dual leg evaluation along the
-    16 local directions + DMMA chain, csrc/quadruped_fused.cuh, DDP_QUAD_LINEARIZE=fused) and the
-    older two-kernel variant (closed-form leg Jacobians, csrc/quadruped_linearize.cuh,
-    DDP_QUAD_STRUCTURED=1) -- against the generic forward-mode-AD kernel on the same points, in
-    contact and in flight, and against the host AD."""
+def test_quadruped_fused_linearization_matches_ad_kernel(monkeypatch):
+    """The fused quadruped linearization (dual leg evaluation along the 16 local directions + DMMA
+    chain, csrc/quadruped_fused.cuh, the default) against the generic forward-mode-AD kernel
+    (DDP_QUAD_LINEARIZE=ad) on the same points, in contact and in flight, and against the host AD."""
     prob = problems.quadruped(60)
     B = 16
     rng = np.random.default_rng(5)
@@ -327,25 +325,21 @@ def test_quadruped_structured_linearization_matches_ad_kernel(monkeypatch):
     x[B // 2:, :, 2] += 0.05                     # second half airborne
     u = prob.u_guess.T[None] + 2.0 * rng.standard_normal((B, prob.N - 1, 12))
     out = {}
-    for mode in ("ad", "structured", "fused"):
-        monkeypatch.delenv("DDP_QUAD_STRUCTURED", raising=False)
-        monkeypatch.setenv("DDP_QUAD_LINEARIZE", "fused" if mode == "fused" else "ad")
-        if mode == "structured":
-            monkeypatch.setenv("DDP_QUAD_STRUCTURED", "1")
+    for mode in ("ad", "fused"):
+        monkeypatch.setenv("DDP_QUAD_LINEARIZE", mode)
         s = make_gpu(prob, B=B)
         s.put(_lib.X_BAR, x)
         s.put(_lib.U_BAR, u)
         s.run_phase(_lib.PHASE_DERIVATIVES)
         out[mode] = (s.get(_lib.FX), s.get(_lib.FU))
     o = make_oracle(prob)
-    for mode in ("structured", "fused"):
-        assert relerr(out[mode][0], out["ad"][0]) < 1e-12, mode
-        assert relerr(out[mode][1], out["ad"][1]) < 1e-12, mode
-        for b in (0, B - 1):
-            for t in (0, 17, 58):
-                fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
-                assert np.abs(out[mode][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max()), mode
-                assert np.abs(out[mode][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max()), mode
+    assert relerr(out["fused"][0], out["ad"][0]) < 1e-12
+    assert relerr(out["fused"][1], out["ad"][1]) < 1e-12
+    for b in (0, B - 1):
+        for t in (0, 17, 58):
+            fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
+            assert np.abs(out["fused"][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max())
+            assert np.abs(out["fused"][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max())
 
 
 def test_backward_newton_schulz_inverse_matches_gauss_jordan(monkeypatch):

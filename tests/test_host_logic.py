@@ -89,3 +89,34 @@ def test_sharded_costs_equal_single_process_gloo():
         o.solve(max_iters=3)
         want.append(o.trace[-1].L)
     np.testing.assert_array_equal(got, np.array(want))
+
+
+def test_drake_system_is_accepted_and_mapped_to_the_analytic_model():
+    """the constructor takes the reference's ``system`` argument -- a discrete-time
+    Drake System, read only through the calls ilqr.py:37-58,725 makes on it -- and selects the
+    matching analytic model.  ShimSystem (the object that lets the unmodified reference run here)
+    duck-types exactly those calls, so it stands in for Drake."""
+    from drake_ddp_b200 import systems
+    from drake_ddp_b200.ilqr import _as_system
+    from oracle.pydrake_shim import ShimSystem
+
+    class Named(ShimSystem):
+        def __init__(self, sysm, name):
+            super().__init__(sysm)
+            self._name = name
+
+        def get_name(self):
+            return self._name
+
+    for sysm, name in ((systems.pendulum(dt=5e-3), "Pendulum"), (systems.acrobot(), "Acrobot"),
+                       (systems.cart_pole(), "CartPole"), (systems.quadruped_quat(), "mini_cheetah"),
+                       (systems.quadruped(), "quadruped"), (systems.arm_ball(), "gen3")):
+        got = _as_system(Named(sysm, name), input_port_index=3)
+        assert (got.model_id, got.n, got.m) == (sysm.model_id, sysm.n, sysm.m)
+        assert got.dt == sysm.dt
+        np.testing.assert_array_equal(got.params, type(got)(got.name, got.model_id, got.n, got.m, sysm.params).params)
+    assert _as_system(systems.pendulum()) is not None          # native descriptor passes through
+    with pytest.raises(TypeError, match="no analytic model"):
+        _as_system(Named(systems.random_affine_sin(6, 2), "mystery"))
+    with pytest.raises(TypeError, match="AnalyticSystem or a discrete-time Drake System"):
+        _as_system(object())

@@ -13,7 +13,7 @@ import pytest
 from drake_ddp_b200 import problems
 from drake_ddp_b200.utils_derivs_interpolation import derivs_interpolation
 from oracle import ilqr_port
-from oracle.make_golden import CASES, run_reference
+from oracle.make_golden import CASES, SOLVE_CASES, run_reference, run_reference_solve
 from oracle.pydrake_shim import reference_available
 from tests.helpers import make_oracle, relerr
 
@@ -79,6 +79,57 @@ def test_full_solve_matches_reference_pendulum():
     assert len(o.trace) == n_iters
     assert abs(Lo - L) <= 1e-10 * abs(L)
     assert relerr(xo.T, x) < 1e-9
+
+
+def solve_case_inputs(name):
+    factory, kp, rows = SOLVE_CASES[name]
+    prob = factory()
+    kpc = prob.keypoints if kp == "problem" else kp
+    nb = max(rows) + 1
+    x0s = prob.batch_x0(nb, seed=0) if prob.sigma > 0 else np.repeat(prob.x0[None], nb, 0)
+    return prob, kpc, rows, x0s
+
+
+@pytest.mark.parametrize("name", sorted(SOLVE_CASES))
+def test_port_full_solve_matches_golden(name):
+    """Whole Solve() to convergence (ilqr.py:669-710, absolute stop rule :692) of the oracle port
+    against the fixtures the UNMODIFIED reference produced for the same (x0, u_guess): same
+    number of iterations, same line-search decisions, final cost within 1e-9 (north star: 1e-5),
+    K, kappa within 1e-6 (north star: 1e-4); line-search failures (the reference's RuntimeError)
+    happen at the same iteration."""
+    prob, kp, rows, x0s = solve_case_inputs(name)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    for b in rows:
+        o = make_oracle(prob, kp=kp, x0=x0s[b])
+        failed = 0
+        try:
+            o.solve()
+        except RuntimeError:
+            failed = 1
+        costs = np.array([r.L for r in o.trace])
+        assert failed == int(g[f"failed_{b}"])
+        assert len(costs) == len(g[f"costs_{b}"]), (b, len(costs), len(g[f"costs_{b}"]))
+        np.testing.assert_array_equal([r.ls_iters for r in o.trace], g[f"ls_iters_{b}"])
+        np.testing.assert_allclose(costs, g[f"costs_{b}"], rtol=1e-9)
+        assert abs(costs[-1] - float(g[f"final_cost_{b}"])) <= 1e-9 * abs(float(g[f"final_cost_{b}"]))
+        assert relerr(o.u_bar.T, g[f"u_bar_{b}"]) < 1e-6
+        if f"K_{b}" in g.files:
+            assert relerr(o.K.transpose(1, 2, 0), g[f"K_{b}"]) < 1e-6
+            assert relerr(o.kappa.T, g[f"kappa_{b}"]) < 1e-6
+
+
+@needs_ref
+def test_full_solve_matches_live_reference_quadruped_n200():
+    """The headline problem (C4: n=36, m=12, N=200) solved to convergence by the unmodified
+    reference, live, against the port: identical iteration count, final cost 1e-9."""
+    prob, kp, rows, x0s = solve_case_inputs("solve_quadruped_N200")
+    b = 3
+    ref = run_reference_solve(prob, kp, x0s[b])
+    o = make_oracle(prob, kp=kp, x0=x0s[b])
+    o.solve()
+    assert len(o.trace) == len(ref["costs"]) and not ref["failed"]
+    assert abs(o.trace[-1].L - ref["final_cost"]) <= 1e-9 * abs(ref["final_cost"])
+    assert relerr(o.K.transpose(1, 2, 0), ref["K"]) < 1e-6
 
 
 @needs_ref
