@@ -28,16 +28,21 @@ SYMBOLS = [
     "ddp_iterate", "ddp_iterate_linesearch", "ddp_iterate_finish_async", "ddp_iterate_wait", "ddp_solve",
     "ddp_run_phase", "ddp_get",
     "ddp_put", "ddp_get_int", "ddp_device_ptr", "ddp_array_elems", "ddp_last_timings",
-    "ddp_launch_count", "ddp_peak_fp64", "ddp_mpc_shift",
+    "ddp_launch_count", "ddp_peak_fp64", "ddp_mpc_shift", "ddp_set_mpc_rearm",
 ]
 
 # enums of include/ddp_b200.h
 X_BAR, U_BAR, K, KAPPA, DV, FX, FU, COST, EPS, IMPROVEMENT, X0, X_NOM = range(12)
-CAND_COST, CAND_EXPECTED, CAND_X, CAND_U = 12, 13, 14, 15
-I_STATUS, I_LS_ITERS, I_ITERS, I_NUM_KEYPOINTS, I_KEYPOINTS, I_ACTIVE = range(6)
+CAND_COST, CAND_EXPECTED, CAND_X, CAND_U, CONVERGED_COST = 12, 13, 14, 15, 16
+I_STATUS, I_LS_ITERS, I_ITERS, I_NUM_KEYPOINTS, I_KEYPOINTS, I_ACTIVE, I_RESOLVES = range(7)
 PHASE_LINESEARCH, PHASE_DERIVATIVES, PHASE_BACKWARD = range(3)
 KP_METHODS = {"setInterval": 0, "adaptiveJerk": 1, "iterativeError": 2}
 TRAJ_RUNNING, TRAJ_CONVERGED, TRAJ_LINESEARCH_FAILED = 0, 1, 2
+
+
+# DMMAs backward_mma_kernel issues per step at (n, m) = (36, 12): the products (8 x 8 tile padding
+# included) + 24 per Newton-Schulz pass, 2.8 passes on average
+BWD_DMMA_PER_STEP_36_12 = 681 + 24 * 2.8
 
 
 def is_stale() -> bool:
@@ -90,6 +95,7 @@ def lib():
     L.ddp_reset.argtypes = [c_vp]
     L.ddp_begin_solve.argtypes = [c_vp]
     L.ddp_mpc_shift.argtypes = [c_vp, c_int]
+    L.ddp_set_mpc_rearm.argtypes = [c_vp, c_int, c_vp]
     L.ddp_set_regularization.argtypes = [c_vp, c_dbl]
     L.ddp_iterate.argtypes = [c_vp, ip]
     L.ddp_iterate_linesearch.argtypes = [c_vp]

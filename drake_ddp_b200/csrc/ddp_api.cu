@@ -113,6 +113,10 @@ void carve(Dev& d, double** params, int np, Carver& c) {
   d.resolved = c.take<int>(B);
   d.acc = c.take<int>(B);
   d.iters = c.take<int>(B);
+  d.rearm = c.take<int>(B);
+  d.resolves = c.take<int>(B);
+  d.L_conv = c.take<double>(B);
+  d.mpc_target_adv_buf = c.take<double>(n);
   d.active_save = c.take<int>(B);
   d.status_save = c.take<int>(B);
   d.counters = c.take<int>(4);
@@ -335,6 +339,10 @@ int iterate_finish_impl(ddp_solver* s) {
   if (rc) return rc;
   CK(cudaEventRecord(s->ev[3], s->stream));
   LAUNCH1(finish_iter_kernel, d);
+  if (d.mpc_replan > 0) {
+    mpc_rearm_kernel<<<d.B, 64, 0, s->stream>>>(d);
+    s->launches++;
+  }
   s->timings_valid = true;
   CK(cudaGetLastError());
   return 0;
@@ -365,6 +373,7 @@ ArrInfo arr(ddp_solver* s, int which) {
     case DDP_IMPROVEMENT: return {d.improvement, B};
     case DDP_X0: return {(void*)d.x0, B * n};
     case DDP_X_NOM: return {(void*)d.x_nom, B * n};
+    case DDP_CONVERGED_COST: return {d.L_conv, B};
     case DDP_CAND_COST: return {d.Lc, B * A};
     case DDP_CAND_EXPECTED: return {d.Ec, B * A};
     case DDP_CAND_X: return {d.xc, B * A * N * n};
@@ -382,6 +391,7 @@ ArrInfo iarr(ddp_solver* s, int which) {
     case DDP_I_NUM_KEYPOINTS: return {d.kpcount, B};
     case DDP_I_KEYPOINTS: return {d.kplist, B * T};
     case DDP_I_ACTIVE: return {d.active, B};
+    case DDP_I_RESOLVES: return {d.resolves, B};
     default: return {nullptr, 0};
   }
 }
@@ -644,6 +654,22 @@ int ddp_mpc_shift(ddp_solver_t* s, int replan_steps) {
   return 0;
 }
 
+int ddp_set_mpc_rearm(ddp_solver_t* s, int replan_steps, const double* target_advance) {
+  GUARD(s);
+  if (replan_steps < 0 || replan_steps >= s->d.N) {
+    g_err = "replan_steps must be in [0, N)";
+    return DDP_ERR_ARG;
+  }
+  s->d.mpc_replan = replan_steps;
+  s->d.mpc_target_adv = nullptr;
+  if (replan_steps > 0 && target_advance) {
+    CK(cudaMemcpyAsync(s->d.mpc_target_adv_buf, target_advance, s->d.n * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->d.mpc_target_adv = s->d.mpc_target_adv_buf;
+  }
+  return 0;
+}
+
 int ddp_begin_solve(ddp_solver_t* s) {
   GUARD(s);
   const int B = s->d.B;
@@ -655,6 +681,8 @@ int ddp_begin_solve(ddp_solver_t* s) {
   CK(cudaMemsetAsync(s->d.status, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.iters, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.ls_iters, 0, B * 4, s->stream));
+  CK(cudaMemsetAsync(s->d.rearm, 0, B * 4, s->stream));
+  CK(cudaMemsetAsync(s->d.resolves, 0, B * 4, s->stream));
   // per-SM CTA-slot bitmasks of the backward sweep: all free between launches; re-zero them in case
   // an earlier launch was aborted with slots taken (they only steer warp roles, never results)
   CK(cudaMemsetAsync(s->d.sm_slots, 0, 1024 * sizeof(int), s->stream));

@@ -25,6 +25,13 @@ struct Dev {
   double *L, *L_new, *eps, *improvement;
   int *ls_iters, *status, *active, *resolved, *acc, *iters, *counters, *unres;
   int *active_save, *status_save;  // ddp_run_phase (teacher-forced tests) puts these back
+  // receding-horizon driver on the device (mini_cheetah.py:147-159,186-206, acrobot.py:131-162):
+  // a trajectory that converges is re-armed as the next MPC resolve instead of being frozen
+  int mpc_replan;          // replan_steps (0: off, a converged trajectory stops iterating)
+  const double* mpc_target_adv;  // [n] added to x_nom of the trajectory at every resolve (moving target)
+  double* mpc_target_adv_buf;
+  int *rearm, *resolves;   // [B] flag for mpc_rearm_kernel; resolves finished so far
+  double* L_conv;          // [B] final cost of the last converged solve
   int bwd_flags;  // bit 0: backward_mma_kernel inverts Quu by Gauss-Jordan at every step (no Newton-Schulz)
   int* sm_slots;  // per-SM bitmask of the CTA slots in use (backward_mma_kernel deals warp roles by slot)
   // keypoints
@@ -308,6 +315,30 @@ __global__ void mpc_shift_kernel(Dev d, int r) {
   for (int j = threadIdx.x; j < n; j += blockDim.x) x0[j] = xr[j];
 }
 
+// The resolve step of the MPC loops for the trajectories finish_iter_kernel flagged: the control
+// tape moves up by r steps and is padded with its last column, x0 <- x_bar[:, r], the target
+// advances (mini_cheetah.py:151-156,193-198).  K, kappa, x_bar, dV stay as they are: the next
+// Solve() on the same object starts from them (stale-state semantics).
+__global__ void mpc_rearm_kernel(Dev d) {
+  const int b = blockIdx.x;
+  if (!d.rearm[b]) return;
+  const int m = d.m, T = d.T, n = d.n, r = d.mpc_replan;
+  double* u = d.u_bar + (size_t)b * T * m;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const double last = u[(size_t)(T - 1) * m + j];
+    for (int t = 0; t < T; ++t) u[(size_t)t * m + j] = (t + r < T) ? u[(size_t)(t + r) * m + j] : last;
+  }
+  double* x0 = const_cast<double*>(d.x0) + (size_t)b * n;
+  double* xnom = const_cast<double*>(d.x_nom) + (size_t)b * n;
+  const double* xr = d.x_bar + ((size_t)b * d.N + r) * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    x0[j] = xr[j];
+    if (d.mpc_target_adv) xnom[j] += d.mpc_target_adv[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) d.rearm[b] = 0;
+}
+
 // reset per-iteration line-search state
 __global__ void begin_iter_kernel(Dev d, int force_all) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,7 +365,16 @@ __global__ void finish_iter_kernel(Dev d) {
   d.iters[b] += 1;
   if (imp > d.delta) {
     atomicAdd(&d.counters[1], 1);
+  } else if (d.mpc_replan > 0) {
+    // Solve() returned; the MPC loop calls it again on the same object for the next resolve
+    d.L_conv[b] = d.L_new[b];
+    d.resolves[b] += 1;
+    d.rearm[b] = 1;
+    d.L[b] = INFINITY;               // ilqr.py:681-682
+    d.improvement[b] = INFINITY;
+    atomicAdd(&d.counters[1], 1);
   } else {
+    d.L_conv[b] = d.L_new[b];
     d.active[b] = 0;
     d.status[b] = 1;
   }

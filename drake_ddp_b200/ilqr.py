@@ -230,6 +230,17 @@ class BatchedILQR:
         pad with the last control, x0 <- x_bar[:, replan_steps] (acrobot.py:145-153)."""
         _lib.check(self._L.ddp_mpc_shift(self._h, int(replan_steps)), "ddp_mpc_shift")
 
+    def set_mpc_rearm(self, replan_steps: int, target_advance=None):
+        """The receding-horizon loop of mini_cheetah.py:186-206 on the device: a trajectory whose
+        Solve() converges is shifted by ``replan_steps`` (x0 <- x_bar[:, r], tape padded, x_nom +=
+        ``target_advance``) and keeps iterating as its next resolve.  0 switches it off."""
+        adv = None
+        if target_advance is not None:
+            adv = np.ascontiguousarray(target_advance, dtype=np.float64)
+            assert adv.shape == (self.n,)
+        _lib.check(self._L.ddp_set_mpc_rearm(self._h, int(replan_steps), None if adv is None else _ptr(adv)),
+                   "ddp_set_mpc_rearm")
+
     # ---- solve ----------------------------------------------------------------------------
     def begin_solve(self):
         _lib.check(self._L.ddp_begin_solve(self._h), "ddp_begin_solve")
@@ -254,8 +265,11 @@ class BatchedILQR:
         _lib.check(self._L.ddp_iterate_wait(self._h, ctypes.byref(n_active)), "ddp_iterate_wait")
         return n_active.value
 
-    def host_exchange(self):
-        return HostExchange(self)
+    def host_exchange(self, replan_steps=None):
+        ex = HostExchange(self)
+        if replan_steps is not None:
+            ex.replan_steps = int(replan_steps)
+        return ex
 
     def solve(self, max_iters=0) -> int:
         it = ctypes.c_int()
@@ -275,6 +289,7 @@ class BatchedILQR:
         _lib.X0: lambda s: (s.B, s.n), _lib.X_NOM: lambda s: (s.B, s.n),
         _lib.CAND_COST: lambda s: (s.B, s.A), _lib.CAND_EXPECTED: lambda s: (s.B, s.A),
         _lib.CAND_X: lambda s: (s.B, s.A, s.N, s.n), _lib.CAND_U: lambda s: (s.B, s.A, s.T, s.m),
+        _lib.CONVERGED_COST: lambda s: (s.B,),
     }
 
     def get(self, which: int) -> np.ndarray:
@@ -363,6 +378,14 @@ class HostExchange:
         self._x0 = solver.device_tensor(_lib.X0)
         self._u = solver.device_tensor(_lib.U_BAR)
         self.ev_applied.record(solver._stream)
+        # re-armed rows (ddp_set_mpc_rearm): host-side shift + patch of the staged upload
+        self.replan_steps = 4
+        self._resolves = np.zeros(solver.B, dtype=np.int32)
+        self._patch_pin = torch.empty((solver.B, solver.T, solver.m), dtype=torch.float64).pin_memory()
+        self._rows_pin = torch.empty(solver.B, dtype=torch.int64).pin_memory()
+        self._patch_dev = torch.empty((solver.B, solver.T, solver.m), dtype=torch.float64, device=dev)
+        self._rows_dev = torch.empty(solver.B, dtype=torch.int64, device=dev)
+        self.d2h_bytes = self.d2h_steps = self.h2d_patch_bytes = 0
 
     def stage_inputs(self, x0_pinned, u_pinned):
         torch = self._torch
@@ -387,9 +410,44 @@ class HostExchange:
         with torch.cuda.stream(self.copy_out):
             u_pinned.copy_(self._u, non_blocking=True)
             self.ev_read.record(self.copy_out)
+        self.d2h_bytes += u_pinned.numel() * 8
+        self.d2h_steps += 1
 
     def wait_controls(self):
         self.ev_read.synchronize()
+
+    def read_rearmed(self, x0_pinned, u_pinned):
+        """With ddp_set_mpc_rearm the device starts the next MPC resolve of every trajectory that
+        converged in this iteration: new x0, shifted tape.  Call after iterate_wait(): reads the
+        resolve counters and x0 back (small), applies the same shift to the re-armed rows of the
+        HOST tape (what the reference's scripts do on the host, mini_cheetah.py:190-198) and patches
+        the staged upload, so host and device keep holding the same closed-loop data."""
+        torch = self._torch
+        s = self.s
+        res = s.get_int(_lib.I_RESOLVES)
+        s.get_into(_lib.X0, x0_pinned)
+        self.d2h_bytes += res.nbytes + x0_pinned.numel() * 8
+        rows = np.nonzero(res != self._resolves)[0]
+        self._resolves = res
+        if rows.size == 0:
+            return 0
+        r = self.replan_steps
+        u = u_pinned.numpy()
+        blk = u[rows]
+        blk[:, :-r] = blk[:, r:].copy()
+        blk[:, -r:] = blk[:, -1:].copy()       # padded with the last control (already moved into place)
+        u[rows] = blk
+        k = rows.size
+        self._patch_pin[:k].copy_(torch.from_numpy(blk))
+        self._rows_pin[:k].copy_(torch.from_numpy(rows.astype(np.int64)))
+        with torch.cuda.stream(self.copy_in):
+            self._patch_dev[:k].copy_(self._patch_pin[:k], non_blocking=True)
+            self._rows_dev[:k].copy_(self._rows_pin[:k], non_blocking=True)
+            self.stage_u.index_copy_(0, self._rows_dev[:k], self._patch_dev[:k])
+            self.stage_x0.copy_(x0_pinned, non_blocking=True)
+            self.ev_staged.record(self.copy_in)
+        self.h2d_patch_bytes += k * (blk.shape[1] * blk.shape[2] * 8 + 8) + x0_pinned.numel() * 8
+        return int(k)
 
 
 class IterativeLinearQuadraticRegulator:

@@ -71,6 +71,7 @@ enum ddp_array {
   DDP_CAND_EXPECTED = 13, /* [B][A] expected improvements of the last round           */
   DDP_CAND_X = 14,        /* [B][A][N][n] candidate rollouts of the last round         */
   DDP_CAND_U = 15,        /* [B][A][T][m]                                              */
+  DDP_CONVERGED_COST = 16, /* [B] return value L of the last Solve() that converged (ilqr.py:710) */
 };
 
 /* int arrays addressable with ddp_get_int */
@@ -81,6 +82,7 @@ enum ddp_int_array {
   DDP_I_NUM_KEYPOINTS = 3, /* [B] len(keyPoints) of the last iteration (ilqr.py:406)  */
   DDP_I_KEYPOINTS = 4,  /* [B][T] ascending keypoint indices, first NUM_KEYPOINTS valid */
   DDP_I_ACTIVE = 5,     /* [B] 1 while the trajectory is still iterating               */
+  DDP_I_RESOLVES = 6,   /* [B] MPC resolves completed on the device (ddp_set_mpc_rearm)  */
 };
 
 /* phases, for teacher-forced checks of one reference function at a time */
@@ -130,6 +132,16 @@ int ddp_reset(ddp_solver_t* s);
  * acrobot.py:145-153 / mini_cheetah.py:190-198): u_bar <- [u_bar[:, r:], last column x r],
  * x0 <- x_bar[:, r] for every trajectory.  K, kappa, x_bar stay (stale-state semantics). */
 int ddp_mpc_shift(ddp_solver_t* s, int replan_steps);
+
+/* The whole receding-horizon loop of mini_cheetah.py:186-206 / acrobot.py:142-160 on the device:
+ * with replan_steps > 0 a trajectory whose Solve() converges (ilqr.py:692) is not frozen; the same
+ * kernel sequence applies ddp_mpc_shift to it alone, adds target_advance [n] (host pointer, may be
+ * NULL) to its x_nom (the moving target of mini_cheetah.py:151-156), sets L = improvement = inf
+ * (ilqr.py:681-682) and the next ddp_iterate is the first iteration of its next resolve -- no
+ * host round trip, every trajectory of the batch keeps iterating.  DDP_I_RESOLVES counts,
+ * DDP_CONVERGED_COST holds the value the last converged Solve() returned.  replan_steps = 0
+ * (default) restores Solve() semantics: converged trajectories stop. */
+int ddp_set_mpc_rearm(ddp_solver_t* s, int replan_steps, const double* target_advance);
 
 /* Solve(), ilqr.py:669-710, split so the host can print the per-iteration table:
  * ddp_begin_solve sets L = inf, improvement = inf for every trajectory (ilqr.py:681-682);

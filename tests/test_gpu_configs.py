@@ -227,3 +227,60 @@ def test_c5_full_solve_final_cost_b512():
     for b in g["rows"]:
         assert abs(cost[b] - float(g[f"final_cost_{b}"])) <= 1e-5 * abs(float(g[f"final_cost_{b}"]))
         assert (s.status[b] == _lib.TRAJ_LINESEARCH_FAILED) == bool(g[f"failed_{b}"])
+
+
+@pytest.mark.parametrize("name", ["acrobot", "quadruped"])
+def test_device_mpc_rearm_matches_reference_mpc_loop(name):
+    """ddp_set_mpc_rearm: the whole receding-horizon loop of mini_cheetah.py:186-206 on the device
+    (a converged trajectory is shifted by replan_steps, its target advances, and it keeps iterating
+    as the next resolve on the same object) against the CPU oracle driven by the reference's host
+    loop, trajectory by trajectory: same resolve boundaries, same costs."""
+    if name == "acrobot":
+        prob, B, replan, n_iter = problems.acrobot(40), 6, 2, 30
+        adv = None
+    else:
+        prob, B, replan, n_iter = problems.quadruped(60), 4, 4, 24
+        adv = np.zeros(36)
+        adv[0] = 1.0 * prob.system.dt * replan
+    x0 = prob.batch_x0(B, seed=5)
+    s = make_gpu(prob, B=B, A=4, x0=x0)
+    s.set_mpc_rearm(replan, adv)
+    s.begin_solve()
+    oracles = [make_oracle(prob, x0=x0[b]) for b in range(B)]
+    Ls = [np.inf] * B
+    resolves = [0] * B
+    dead = [False] * B
+    for it in range(n_iter):
+        n_active = s.iterate()
+        cost, conv = s.cost, s.get(_lib.CONVERGED_COST)
+        got_res = s.get_int(_lib.I_RESOLVES)
+        for b, o in enumerate(oracles):
+            if dead[b]:
+                continue
+            try:
+                rec = o.iterate(Ls[b])
+            except RuntimeError:
+                dead[b] = True
+                assert s.status[b] == _lib.TRAJ_LINESEARCH_FAILED
+                continue
+            Ls[b] = rec.L
+            if rec.improvement <= prob.delta:                  # Solve() returned: next resolve
+                resolves[b] += 1
+                assert abs(conv[b] - rec.L) <= 1e-6 * abs(rec.L), (it, b)
+                assert np.isinf(cost[b])                       # L = inf at the start of a solve
+                u = o.u_bar.T
+                o.set_initial_guess(np.block([u[:, replan:], np.repeat(u[:, -1][np.newaxis].T, replan, axis=1)]))
+                o.set_initial_state(o.x_bar[replan])
+                if adv is not None:
+                    o.set_target_state(o.x_nom + adv)
+                Ls[b] = np.inf
+            else:
+                assert abs(cost[b] - rec.L) <= 1e-6 * abs(rec.L), (it, b, cost[b], rec.L)
+            assert got_res[b] == resolves[b], (it, b)
+        assert n_active == B - sum(dead)
+    assert sum(resolves) >= B                                  # every trajectory re-solved at least once on average
+    for b, o in enumerate(oracles):
+        if not dead[b]:
+            assert relerr(s.get(_lib.U_BAR)[b], o.u_bar) < 1e-5
+            np.testing.assert_allclose(s.get(_lib.X0)[b], o.x0, rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(s.get(_lib.X_NOM)[b], o.x_nom, rtol=1e-12, atol=1e-12)
