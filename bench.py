@@ -398,9 +398,9 @@ def run_b200(args):
         ex.read_controls(u_pin)               # tape of this iteration, under derivatives + backward
         solver.iterate_finish_async()
         ex.wait_controls()
+        ex.stage_inputs(x0_pin, u_pin)        # next upload travels under the backward pass
         n_act = solver.iterate_wait()
-        ex.read_rearmed(x0_pin, u_pin)        # re-armed trajectories: new x0 / shifted tape
-        ex.stage_inputs(x0_pin, u_pin)
+        ex.read_rearmed(x0_pin, u_pin)        # re-armed trajectories: new x0, shifted tape rows patched
         gather_costs()
         solver.get_into(_lib.COST, cost_pin)
         return n_act

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DDP_B200_LIB") or os.path.join(_HERE, "libddp_b200.so")
 _CSRC = os.path.join(_HERE, "csrc")
 _SOURCES = [os.path.join(_CSRC, "ddp_api.cu")]
-_DEPS = _SOURCES + [os.path.join(_CSRC, f) for f in ("kernels.cuh", "backward_mma.cuh", "quadruped_fused.cuh", "quadruped_rollout.cuh", "models.h", "dual.h")] + [
+_DEPS = _SOURCES + [os.path.join(_CSRC, f) for f in ("kernels.cuh", "backward_sym.cuh", "quadruped_fused.cuh", "quadruped_rollout.cuh", "models.h", "dual.h")] + [
     os.path.join(_HERE, "..", "include", "ddp_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -40,7 +40,7 @@ KP_METHODS = {"setInterval": 0, "adaptiveJerk": 1, "iterativeError": 2}
 TRAJ_RUNNING, TRAJ_CONVERGED, TRAJ_LINESEARCH_FAILED = 0, 1, 2
 
 
-# DMMAs backward_mma_kernel issues per step at (n, m) = (36, 12): the products (8 x 8 tile padding
+# DMMAs backward_sym_kernel issues per step at (n, m) = (36, 12): the products (8 x 8 tile padding
 # included) + 24 per Newton-Schulz pass, 2.8 passes on average
 BWD_DMMA_PER_STEP_36_12 = 681 + 24 * 2.8
 

@@ -12,7 +12,7 @@
 
 #include "../../include/ddp_b200.h"
 #include "kernels.cuh"
-#include "backward_mma.cuh"
+#include "backward_sym.cuh"
 #include "quadruped_fused.cuh"
 #include "quadruped_rollout.cuh"
 
@@ -34,7 +34,7 @@ struct ddp_solver {
   Dev d;
   cudaStream_t stream;
   // per-solver (hence per-device) launch configuration, set on first use
-  bool cfg_bwd_mma, cfg_bwd;
+  bool cfg_bwd, cfg_bwd_sym;
   int fused_ctas;
   std::vector<double> eps_host;
   double beta;
@@ -161,26 +161,26 @@ int launch_linearize(ddp_solver* s, const int* list, const int* count) {
   return 0;
 }
 template <class Model>
-int launch_backward_mma(ddp_solver* s) {
-  typedef BwdMmaCfg<Model::n, Model::m> C;
-  const size_t smem = sizeof(BwdMmaSmem<Model::n, Model::m>);
-  if (!s->cfg_bwd_mma) {
-    cudaError_t e = cudaFuncSetAttribute(backward_mma_kernel<Model>,
+int launch_backward_sym(ddp_solver* s) {
+  typedef BsCfg<Model::n, Model::m> C;
+  const size_t smem = sizeof(BsSmem<Model::n, Model::m>);
+  if (!s->cfg_bwd_sym) {
+    cudaError_t e = cudaFuncSetAttribute(backward_sym_kernel<Model>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
-      g_err = std::string("cudaFuncSetAttribute(backward_mma): ") + cudaGetErrorString(e);
+      g_err = std::string("cudaFuncSetAttribute(backward_sym): ") + cudaGetErrorString(e);
       return DDP_ERR_CUDA;
     }
-    s->cfg_bwd_mma = true;
+    s->cfg_bwd_sym = true;
   }
-  backward_mma_kernel<Model><<<s->d.B, C::NT, smem, s->stream>>>(s->d);
+  backward_sym_kernel<Model><<<s->d.B, C::NT, smem, s->stream>>>(s->d);
   s->launches++;
   return 0;
 }
 template <class Model>
 int launch_backward(ddp_solver* s) {
   if constexpr (Model::n >= 16) {
-    if (!s->scalar_backward) return launch_backward_mma<Model>(s);
+    if (!s->scalar_backward) return launch_backward_sym<Model>(s);
   }
   constexpr int NT = Cfg<Model>::BWD_THREADS;
   const size_t smem = sizeof(BwdSmem<Model::n, Model::m>);
@@ -456,7 +456,7 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   s->stream = (cudaStream_t)stream;
   s->launches = 0;
   s->timings_valid = false;
-  s->cfg_bwd_mma = s->cfg_bwd = false;
+  s->cfg_bwd = s->cfg_bwd_sym = false;
   s->fused_ctas = 0;
   s->h_counters = nullptr;
   for (int i = 0; i < 4; ++i) s->ev[i] = nullptr;
@@ -862,18 +862,10 @@ int ddp_debug_roll_profile(long long* out16) {
 }
 #endif
 #ifdef DDP_BWD_PROFILE
-// debug builds only: per-phase cycle totals recorded by backward_mma_kernel
-int ddp_debug_bwd_profile(long long* out64) {
+// debug builds only: per-phase cycle totals recorded by backward_sym_kernel
+int ddp_debug_bwd_profile(long long* out128) {
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpyFromSymbol(out64, ddp::g_bwd_prof, sizeof(long long) * 128));
-  int fb = 0, zero = 0;
-  CK(cudaMemcpyFromSymbol(&fb, ddp::g_bwd_fallbacks, sizeof(int)));
-  CK(cudaMemcpyToSymbol(ddp::g_bwd_fallbacks, &zero, sizeof(int)));
-  out64[127] = fb;
-  int ps = 0;
-  CK(cudaMemcpyFromSymbol(&ps, ddp::g_bwd_passes, sizeof(int)));
-  CK(cudaMemcpyToSymbol(ddp::g_bwd_passes, &zero, sizeof(int)));
-  out64[126] = ps;
+  CK(cudaMemcpyFromSymbol(out128, ddp::g_bwd_prof, sizeof(long long) * 128));
   return 0;
 }
 #endif

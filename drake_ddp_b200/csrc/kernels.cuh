@@ -32,8 +32,8 @@ struct Dev {
   double* mpc_target_adv_buf;
   int *rearm, *resolves;   // [B] flag for mpc_rearm_kernel; resolves finished so far
   double* L_conv;          // [B] final cost of the last converged solve
-  int bwd_flags;  // bit 0: backward_mma_kernel inverts Quu by Gauss-Jordan at every step (no Newton-Schulz)
-  int* sm_slots;  // per-SM bitmask of the CTA slots in use (backward_mma_kernel deals warp roles by slot)
+  int bwd_flags;  // bit 0: backward_sym_kernel inverts Quu by Gauss-Jordan at every step (no Newton-Schulz)
+  int* sm_slots;  // per-SM bitmask of the CTA slots in use (backward_sym_kernel deals warp roles by slot)
   // keypoints
   int kp_method, minN, maxN;
   double jerk_thr, err_thr;

@@ -19,7 +19,7 @@
 // and the host AD (tests/test_gpu_parity.py).  Two substeps only (the model's setting); other
 // settings use the generic kernel.
 #pragma once
-#include "backward_mma.cuh"
+#include "backward_sym.cuh"
 
 namespace ddp {
 
@@ -53,6 +53,9 @@ struct QfWarpSmem {
 #ifndef QF_MAXNREG
 #define QF_MAXNREG 0
 #endif
+#ifndef QF_ND
+#define QF_ND 2      // seed directions a lane carries per pass (2: one pass; 1: two passes, fewer registers)
+#endif
 #if QF_MAXNREG
 __global__ void __maxnreg__(QF_MAXNREG)
 #else
@@ -60,7 +63,8 @@ __global__ void __launch_bounds__(kQfWarps * 32, QF_MINB)
 #endif
 quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   typedef Quadruped Qd;
-  typedef Dual<2> D2;
+  constexpr int ND = QF_ND, NPASS = 2 / ND;
+  typedef Dual<ND> D2;
   constexpr int LD = kQfLd;
   extern __shared__ __align__(16) unsigned char qf_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -73,8 +77,6 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
 
   // lane -> (leg, pair of local directions) and the global columns of the two directions
   const int leg = lane >> 3, dp = lane & 7;
-  const int j0 = 2 * dp, j1 = j0 + 1;
-  const int gc[2] = {qf_gcol(leg, j0), qf_gcol(leg, j1)};
   const bool shared_dir = dp < 5;   // base directions: every leg contributes to the base rows
   const double sx = (leg < 2) ? 1.0 : -1.0, sd = (leg & 1) ? 1.0 : -1.0;
 
@@ -139,14 +141,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       const double* xin = s.st[sub];
       double* xout = s.st[sub + 1];
       double* Dv = (sub == 0) ? s.D1v : s.D2v;   // 18 x 48 velocity rows of this substep
-      // ---- dual evaluation of this lane's leg along its two local directions -----------------
-      auto seed = [&](double v, int j) {
-        D2 r;
-        r.v = v;
-        r.d[0] = (j == j0) ? 1.0 : 0.0;
-        r.d[1] = (j == j1) ? 1.0 : 0.0;
-        return r;
-      };
+      // ---- dual evaluation of this lane's leg along its two local directions (ND per pass) -------
       // one sincos per lane, shared by shuffle: lanes dp = 0..2 of a leg group take abad, hip,
       // hip + knee of their leg, dp = 3..5 roll, pitch, yaw (same values in every group)
       double sn, cs;
@@ -159,72 +154,96 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
                                        : xin[5];
         sincos_(ang, &sn, &cs);
       }
-      // dual sine / cosine of an angle whose value pair comes from lane `src` and whose seed
-      // weights along this lane's two directions are w0, w1
-      auto trig_dual = [&](int src, double w0, double w1, D2& sD, D2& cD) {
-        const double sv = __shfl_sync(full, sn, src), cv = __shfl_sync(full, cs, src);
-        sD.v = sv; sD.d[0] = cv * w0; sD.d[1] = cv * w1;
-        cD.v = cv; cD.d[0] = -sv * w0; cD.d[1] = -sv * w1;
-      };
-      auto w = [&](int j, int e) { return (j == (e ? j1 : j0)) ? 1.0 : 0.0; };
       const int gl = lane & ~7;   // first lane of this leg's group
-      D2 vb[6];
+      double f[6], av[3], vbv[6];
+#pragma unroll 1
+      for (int pass = 0; pass < NPASS; ++pass) {
+        int jd[ND], gc[ND];      // local directions of this pass and their global columns
 #pragma unroll
-      for (int k = 0; k < 6; ++k) vb[k] = seed(xin[18 + k], 4 + k);
-      const D2 pz = seed(xin[2], 0);
-      Qd::BasePose<D2> B;
-      D2 sy, cy;
-      trig_dual(gl + 3, w(1, 0), w(1, 1), B.sr, B.cr);
-      trig_dual(gl + 4, w(2, 0), w(2, 1), B.sp, B.cp);
-      trig_dual(gl + 5, w(3, 0), w(3, 1), sy, cy);
-      Qd::base_pose_trig(sy, cy, B);
-      trig[sub][0] = B.sr.v; trig[sub][1] = B.cr.v; trig[sub][2] = B.sp.v; trig[sub][3] = B.cp.v;
-      D2 sa, ca, sh, ch, sk, ck;
-      trig_dual(gl + 0, w(10, 0), w(10, 1), sa, ca);
-      trig_dual(gl + 1, w(11, 0), w(11, 1), sh, ch);
-      trig_dual(gl + 2, w(11, 0) + w(12, 0), w(11, 1) + w(12, 1), sk, ck);
-      Qd::LegOut<D2> o;
-      Qd::leg_trig(sx, sd, sa, ca, sh, ch, sk, ck, seed(xin[24 + 3 * leg], 13), seed(xin[25 + 3 * leg], 14),
-                   seed(xin[26 + 3 * leg], 15), D2(ua), D2(uh), D2(uk), pz, vb, B, p, o);
-      // ---- scatter: joint rows of this leg, base rows summed over the legs ---------------------
-      {
-        const D2* ja[3] = {&o.a0, &o.a1, &o.a2};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int r = 6 + 3 * leg + k;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) Dv[r * LD + gc[e]] = h * ja[k]->d[e] + ((gc[e] == 18 + r) ? 1.0 : 0.0);
+        for (int e = 0; e < ND; ++e) {
+          jd[e] = 2 * dp + pass * ND + e;
+          gc[e] = qf_gcol(leg, jd[e]);
         }
-        const D2* fo[6] = {&o.Fx, &o.Fy, &o.Fz, &o.Tx, &o.Ty, &o.Tz};
-        const double inv[6] = {1.0 / mass, 1.0 / mass, 1.0 / mass, 1.0 / Ix, 1.0 / Iy, 1.0 / Iz};
+        auto seed = [&](double v, int j) {
+          D2 r;
+          r.v = v;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
+          for (int e = 0; e < ND; ++e) r.d[e] = (j == jd[e]) ? 1.0 : 0.0;
+          return r;
+        };
+        // dual sine / cosine of an angle whose value pair comes from lane `src`; the angle is local
+        // input ja (+ jb for hip + knee)
+        auto trig_dual = [&](int src, int ja, int jb, D2& sD, D2& cD) {
+          const double sv = __shfl_sync(full, sn, src), cv = __shfl_sync(full, cs, src);
+          sD.v = sv;
+          cD.v = cv;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            double own = fo[r]->d[e], sum = own;
-            sum += __shfl_xor_sync(full, sum, 8);
-            sum += __shfl_xor_sync(full, sum, 16);
-            const double gs = shared_dir ? sum : own;
-            if (!shared_dir || leg == 0) Dv[r * LD + gc[e]] = (h * inv[r]) * gs + ((gc[e] == 18 + r) ? 1.0 : 0.0);
+          for (int e = 0; e < ND; ++e) {
+            const double we = ((jd[e] == ja) || (jd[e] == jb)) ? 1.0 : 0.0;
+            sD.d[e] = cv * we;
+            cD.d[e] = -sv * we;
           }
+        };
+        D2 vb[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vb[k] = seed(xin[18 + k], 4 + k);
+        const D2 pz = seed(xin[2], 0);
+        Qd::BasePose<D2> B;
+        D2 sy, cy;
+        trig_dual(gl + 3, 1, -1, B.sr, B.cr);
+        trig_dual(gl + 4, 2, -1, B.sp, B.cp);
+        trig_dual(gl + 5, 3, -1, sy, cy);
+        Qd::base_pose_trig(sy, cy, B);
+        trig[sub][0] = B.sr.v; trig[sub][1] = B.cr.v; trig[sub][2] = B.sp.v; trig[sub][3] = B.cp.v;
+        D2 sa, ca, sh, ch, sk, ck;
+        trig_dual(gl + 0, 10, -1, sa, ca);
+        trig_dual(gl + 1, 11, -1, sh, ch);
+        trig_dual(gl + 2, 11, 12, sk, ck);
+        Qd::LegOut<D2> o;
+        Qd::leg_trig(sx, sd, sa, ca, sh, ch, sk, ck, seed(xin[24 + 3 * leg], 13), seed(xin[25 + 3 * leg], 14),
+                     seed(xin[26 + 3 * leg], 15), D2(ua), D2(uh), D2(uk), pz, vb, B, p, o);
+        // ---- scatter: joint rows of this leg, base rows summed over the legs -------------------
+        {
+          const D2* ja[3] = {&o.a0, &o.a1, &o.a2};
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int r = 6 + 3 * leg + k;
+#pragma unroll
+            for (int e = 0; e < ND; ++e) Dv[r * LD + gc[e]] = h * ja[k]->d[e] + ((gc[e] == 18 + r) ? 1.0 : 0.0);
+          }
+          const D2* fo[6] = {&o.Fx, &o.Fy, &o.Fz, &o.Tx, &o.Ty, &o.Tz};
+          const double inv[6] = {1.0 / mass, 1.0 / mass, 1.0 / mass, 1.0 / Ix, 1.0 / Iy, 1.0 / Iz};
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+#pragma unroll
+            for (int e = 0; e < ND; ++e) {
+              double own = fo[r]->d[e], sum = own;
+              sum += __shfl_xor_sync(full, sum, 8);
+              sum += __shfl_xor_sync(full, sum, 16);
+              const double gs = shared_dir ? sum : own;
+              if (!shared_dir || leg == 0) Dv[r * LD + gc[e]] = (h * inv[r]) * gs + ((gc[e] == 18 + r) ? 1.0 : 0.0);
+            }
+          }
+        }
+        if (pass == NPASS - 1) {
+          f[0] = o.Fx.v; f[1] = o.Fy.v; f[2] = o.Fz.v; f[3] = o.Tx.v; f[4] = o.Ty.v; f[5] = o.Tz.v;
+          av[0] = o.a0.v; av[1] = o.a1.v; av[2] = o.a2.v;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) vbv[k] = vb[k].v;
         }
       }
       // ---- primal state after the substep (same arithmetic as Quadruped::integrate) ------------
-      double f[6] = {o.Fx.v, o.Fy.v, o.Fz.v, o.Tx.v, o.Ty.v, o.Tz.v};
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         f[k] += __shfl_xor_sync(full, f[k], 8);
         f[k] += __shfl_xor_sync(full, f[k], 16);
       }
-      double vcur[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) vcur[k] = vb[k].v;
       double accb[18];
-      Qd::base_acc(f[0], f[1], f[2], f[3], f[4], f[5], vcur, p, accb);
+      Qd::base_acc(f[0], f[1], f[2], f[3], f[4], f[5], vbv, p, accb);
       {
         const int jl = (lane >= 6 && lane < 18) ? (lane - 6) / 3 : 0, jk = (lane >= 6 && lane < 18) ? (lane - 6) % 3 : 0;
-        const double a0 = __shfl_sync(full, o.a0.v, 8 * jl), a1 = __shfl_sync(full, o.a1.v, 8 * jl),
-                     a2 = __shfl_sync(full, o.a2.v, 8 * jl);
+        const double a0 = __shfl_sync(full, av[0], 8 * jl), a1 = __shfl_sync(full, av[1], 8 * jl),
+                     a2 = __shfl_sync(full, av[2], 8 * jl);
         double acc = (jk == 0) ? a0 : ((jk == 1) ? a1 : a2);
 #pragma unroll
         for (int k = 0; k < 6; ++k)

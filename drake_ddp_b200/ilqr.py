@@ -425,10 +425,14 @@ class HostExchange:
         torch = self._torch
         s = self.s
         res = s.get_int(_lib.I_RESOLVES)
+        self.ev_staged.synchronize()           # the staged upload has finished reading the pinned buffers
         s.get_into(_lib.X0, x0_pinned)
         self.d2h_bytes += res.nbytes + x0_pinned.numel() * 8
         rows = np.nonzero(res != self._resolves)[0]
         self._resolves = res
+        with torch.cuda.stream(self.copy_in):
+            self.stage_x0.copy_(x0_pinned, non_blocking=True)
+            self.ev_staged.record(self.copy_in)
         if rows.size == 0:
             return 0
         r = self.replan_steps
@@ -444,7 +448,6 @@ class HostExchange:
             self._patch_dev[:k].copy_(self._patch_pin[:k], non_blocking=True)
             self._rows_dev[:k].copy_(self._rows_pin[:k], non_blocking=True)
             self.stage_u.index_copy_(0, self._rows_dev[:k], self._patch_dev[:k])
-            self.stage_x0.copy_(x0_pinned, non_blocking=True)
             self.ev_staged.record(self.copy_in)
         self.h2d_patch_bytes += k * (blk.shape[1] * blk.shape[2] * 8 + 8) + x0_pinned.numel() * 8
         return int(k)

@@ -42,9 +42,9 @@ for name in phases:
     ts = []
     for r in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(s._stream)
         s.run_phase(PH[name])
-        e1.record()
+        e1.record(s._stream)
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     out[name] = round(float(np.median(ts)), 4)
