@@ -884,6 +884,13 @@ backward_sym_kernel(Dev d) {
   }
   __syncthreads();
   const int slot = s.slot;
+#ifdef DDP_BWD_STAGGER
+  {   // experiment: offset the CTAs of an SM by a fraction of a step
+    const long long until = clock64() + (long long)slot * DDP_BWD_STAGGER;
+    while (clock64() < until) {
+    }
+  }
+#endif
   const int role = (warp - slot - 1) & 3;   // 0..2: DMMA warps; 3 (warp == slot): the vector warp
   if (C::TMA) {
     if (role == NMW && lane == 0) {

@@ -156,8 +156,12 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       }
       const int gl = lane & ~7;   // first lane of this leg's group
       double f[6], av[3], vbv[6];
+#ifdef QF_SKIP_LEG
+      for (int pass = 0; pass < 0; ++pass) {
+#else
 #pragma unroll 1
       for (int pass = 0; pass < NPASS; ++pass) {
+#endif
         int jd[ND], gc[ND];      // local directions of this pass and their global columns
 #pragma unroll
         for (int e = 0; e < ND; ++e) {
@@ -282,6 +286,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       }
     }
 
+#ifndef QF_SKIP_CHAIN
     // ---- chain ----------------------------------------------------------------------------------
     // With Dv2 = [Aq | Av | Au] (18 x (18+18+12)), D1v the velocity rows of substep 1 and
     // D1q = E1 + h N1 D1v its position rows (E1 = [I + h M1 | 0 | 0], N1 the Euler-rate matrix):
@@ -409,6 +414,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       }
     }
     __syncwarp();
+#endif
     }
     ok = nok;
     b = nb;
