@@ -156,9 +156,13 @@ DDP_HD S sphere_plane_force(const S& depth, double R, double E) {
 //   q = [px py pz | roll pitch yaw | (abad hip knee) x {FR, FL, HR, HL}]   (18)
 //   v = [world linear velocity | body angular velocity | joint rates]        (18)
 // p = [dt, substeps, mass, Ixx, Iyy, Izz, Ij_abad, Ij_hip, Ij_knee, joint_damping,
-//      l_abad, l_thigh, l_shank, hip_x, hip_y, foot_radius, E, mu, v_stiction, g]
+//      l_abad, l_thigh, l_shank, hip_x, hip_y, foot_radius, E, mu, v_stiction, g,
+//      1/mass, 1/Ixx, 1/Iyy, 1/Izz, 1/Ij_abad, 1/Ij_hip, 1/Ij_knee]
+// The model divides by nothing but cos(pitch) and the slip speed: masses and inertias enter through
+// their reciprocals (p[20..26], rounded once on the host), because an fp64 division is ~25 dependent
+// instructions on the serial path of every rollout step.
 struct Quadruped {
-  static constexpr int n = 36, m = 12, np = 20;
+  static constexpr int n = 36, m = 12, np = 27;
   static constexpr int COOP = 4;  // step_coop: one leg per lane of a 4-lane group
 
   template <class S>
@@ -231,9 +235,10 @@ struct Quadruped {
       S wx = v[0] + B.R00 * bx + B.R01 * by + B.R02 * bz;
       S wy = v[1] + B.R10 * bx + B.R11 * by + B.R12 * bz;
       S Fn = sphere_plane_force(depth, rf, E);
-      S sl = sqrt_(wx * wx + wy * wy + vs * vs);
-      S ftx = -(mu * Fn) * wx / sl;
-      S fty = -(mu * Fn) * wy / sl;
+      S isl = 1.0 / sqrt_(wx * wx + wy * wy + vs * vs);
+      S ftn = (mu * Fn) * isl;
+      S ftx = -(ftn * wx);
+      S fty = -(ftn * wy);
       o.Fx = ftx; o.Fy = fty; o.Fz = Fn;
       S fbx = B.R00 * ftx + B.R10 * fty + B.R20 * Fn;   // force in body frame
       S fby = B.R01 * ftx + B.R11 * fty + B.R21 * Fn;
@@ -245,9 +250,9 @@ struct Quadruped {
       tau1 = J01 * fbx + J11 * fby + J21 * fbz;
       tau2 = J02 * fbx + J12 * fby + J22 * fbz;
     }
-    o.a0 = (ua + tau0 - bj * va) / p[6];
-    o.a1 = (uh + tau1 - bj * vh) / p[7];
-    o.a2 = (uk + tau2 - bj * vk) / p[8];
+    o.a0 = (ua + tau0 - bj * va) * p[24];
+    o.a1 = (uh + tau1 - bj * vh) * p[25];
+    o.a2 = (uk + tau2 - bj * vk) * p[26];
   }
   // base accelerations from the summed leg loads, then the semi-implicit Euler update
   template <class S>
@@ -258,24 +263,25 @@ struct Quadruped {
     q[0] = q[0] + h * v[0];
     q[1] = q[1] + h * v[1];
     q[2] = q[2] + h * v[2];
-    S tp = B.sp / B.cp;
+    S icp = 1.0 / B.cp;
+    S tp = B.sp * icp;
     S wyz = B.sr * v[4] + B.cr * v[5];
     q[3] = q[3] + h * (v[3] + tp * wyz);
     q[4] = q[4] + h * (B.cr * v[4] - B.sr * v[5]);
-    q[5] = q[5] + h * (wyz / B.cp);
+    q[5] = q[5] + h * (wyz * icp);
 #pragma unroll
     for (int i = 6; i < 18; ++i) q[i] = q[i] + h * v[i];
   }
   template <class S>
   DDP_HD static void base_acc(const S& Fx, const S& Fy, const S& Fz, const S& Tx, const S& Ty, const S& Tz,
                               const S* v, const double* p, S* acc) {
-    const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5], g = p[19];
-    acc[0] = Fx / mass;
-    acc[1] = Fy / mass;
-    acc[2] = Fz / mass - g;
-    acc[3] = (Tx - (Iz - Iy) * v[4] * v[5]) / Ix;
-    acc[4] = (Ty - (Ix - Iz) * v[5] * v[3]) / Iy;
-    acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) / Iz;
+    const double Ix = p[3], Iy = p[4], Iz = p[5], g = p[19];
+    acc[0] = Fx * p[20];
+    acc[1] = Fy * p[20];
+    acc[2] = Fz * p[20] - g;
+    acc[3] = (Tx - (Iz - Iy) * v[4] * v[5]) * p[21];
+    acc[4] = (Ty - (Ix - Iz) * v[5] * v[3]) * p[22];
+    acc[5] = (Tz - (Iy - Ix) * v[3] * v[4]) * p[23];
   }
 
   // one semi-implicit Euler substep of length h, in place.  Leg loads are summed pairwise,
@@ -408,7 +414,7 @@ struct Quadruped {
 // The rotation uses the normalised quaternion; the state itself is not renormalised.
 // Same parameter vector as Quadruped.
 struct QuadrupedQuat {
-  static constexpr int n = 37, m = 12, np = 20;
+  static constexpr int n = 37, m = 12, np = 27;
   static constexpr int COOP = 4;  // step_coop: one leg per lane of a 4-lane group
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
@@ -432,8 +438,8 @@ struct QuadrupedQuat {
     }
     for (int it = 0; it < sub; ++it) {
       // rotation matrix of the normalised quaternion (body -> world)
-      S nn = sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
-      S a = qt[0] / nn, b = qt[1] / nn, c = qt[2] / nn, d = qt[3] / nn;
+      S inn = 1.0 / sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+      S a = qt[0] * inn, b = qt[1] * inn, c = qt[2] * inn, d = qt[3] * inn;
       Qd::BasePose<S> B;
       B.R00 = 1.0 - 2.0 * (c * c + d * d); B.R01 = 2.0 * (b * c - a * d); B.R02 = 2.0 * (b * d + a * c);
       B.R10 = 2.0 * (b * c + a * d); B.R11 = 1.0 - 2.0 * (b * b + d * d); B.R12 = 2.0 * (c * d - a * b);
@@ -463,15 +469,15 @@ struct QuadrupedQuat {
       }
       // body-frame Euler equations, then back to the world frame: wdot_W = R wdot_B
       S Tx = sum[0][3] + sum[1][3], Ty = sum[0][4] + sum[1][4], Tz = sum[0][5] + sum[1][5];
-      S ab0 = (Tx - (Iz - Iy) * vloc[4] * vloc[5]) / Ix;
-      S ab1 = (Ty - (Ix - Iz) * vloc[5] * vloc[3]) / Iy;
-      S ab2 = (Tz - (Iy - Ix) * vloc[3] * vloc[4]) / Iz;
+      S ab0 = (Tx - (Iz - Iy) * vloc[4] * vloc[5]) * p[21];
+      S ab1 = (Ty - (Ix - Iz) * vloc[5] * vloc[3]) * p[22];
+      S ab2 = (Tz - (Iy - Ix) * vloc[3] * vloc[4]) * p[23];
       w[0] = w[0] + h * (B.R00 * ab0 + B.R01 * ab1 + B.R02 * ab2);
       w[1] = w[1] + h * (B.R10 * ab0 + B.R11 * ab1 + B.R12 * ab2);
       w[2] = w[2] + h * (B.R20 * ab0 + B.R21 * ab1 + B.R22 * ab2);
-      vl[0] = vl[0] + h * ((sum[0][0] + sum[1][0]) / p[2]);
-      vl[1] = vl[1] + h * ((sum[0][1] + sum[1][1]) / p[2]);
-      vl[2] = vl[2] + h * ((sum[0][2] + sum[1][2]) / p[2] - p[19]);
+      vl[0] = vl[0] + h * ((sum[0][0] + sum[1][0]) * p[20]);
+      vl[1] = vl[1] + h * ((sum[0][1] + sum[1][1]) * p[20]);
+      vl[2] = vl[2] + h * ((sum[0][2] + sum[1][2]) * p[20] - p[19]);
 #pragma unroll
       for (int i = 0; i < 12; ++i) vj[i] = vj[i] + h * aj[i];
       // qdot = 0.5 * (0, w_W) (x) q
@@ -529,8 +535,8 @@ struct QuadrupedQuat {
     const double uk = Qd::pick4(lane, u[2], u[5], u[8], u[11]);
     const double sx = (lane < 2) ? 1.0 : -1.0, sd = (lane & 1) ? 1.0 : -1.0;
     for (int it = 0; it < sub; ++it) {
-      double nn = sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
-      double a = qt[0] / nn, b = qt[1] / nn, c = qt[2] / nn, d = qt[3] / nn;
+      double inn = 1.0 / sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+      double a = qt[0] * inn, b = qt[1] * inn, c = qt[2] * inn, d = qt[3] * inn;
       Qd::BasePose<double> B;
       B.R00 = 1.0 - 2.0 * (c * c + d * d); B.R01 = 2.0 * (b * c - a * d); B.R02 = 2.0 * (b * d + a * c);
       B.R10 = 2.0 * (b * c + a * d); B.R11 = 1.0 - 2.0 * (b * b + d * d); B.R12 = 2.0 * (c * d - a * b);
@@ -559,15 +565,15 @@ struct QuadrupedQuat {
         aj[3 * l + 1] = __shfl_sync(mask, o.a1, gbase + l);
         aj[3 * l + 2] = __shfl_sync(mask, o.a2, gbase + l);
       }
-      double ab0 = (f[3] - (Iz - Iy) * vloc[4] * vloc[5]) / Ix;
-      double ab1 = (f[4] - (Ix - Iz) * vloc[5] * vloc[3]) / Iy;
-      double ab2 = (f[5] - (Iy - Ix) * vloc[3] * vloc[4]) / Iz;
+      double ab0 = (f[3] - (Iz - Iy) * vloc[4] * vloc[5]) * p[21];
+      double ab1 = (f[4] - (Ix - Iz) * vloc[5] * vloc[3]) * p[22];
+      double ab2 = (f[5] - (Iy - Ix) * vloc[3] * vloc[4]) * p[23];
       w[0] = w[0] + h * (B.R00 * ab0 + B.R01 * ab1 + B.R02 * ab2);
       w[1] = w[1] + h * (B.R10 * ab0 + B.R11 * ab1 + B.R12 * ab2);
       w[2] = w[2] + h * (B.R20 * ab0 + B.R21 * ab1 + B.R22 * ab2);
-      vl[0] = vl[0] + h * (f[0] / p[2]);
-      vl[1] = vl[1] + h * (f[1] / p[2]);
-      vl[2] = vl[2] + h * (f[2] / p[2] - p[19]);
+      vl[0] = vl[0] + h * (f[0] * p[20]);
+      vl[1] = vl[1] + h * (f[1] * p[20]);
+      vl[2] = vl[2] + h * (f[2] * p[20] - p[19]);
 #pragma unroll
       for (int i = 0; i < 12; ++i) vj[i] = vj[i] + h * aj[i];
       double q0 = qt[0], q1 = qt[1], q2 = qt[2], q3 = qt[3];

@@ -72,7 +72,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   const unsigned full = 0xffffffffu;
   const double* p = d.params;
   const double h = p[0] / 2.0;
-  const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5];
+  const double Ix = p[3], Iy = p[4], Iz = p[5];
   const int T = d.T;
 
   // lane -> (leg, pair of local directions) and the global columns of the two directions
@@ -86,8 +86,8 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   for (int i = lane; i < 18 * LD; i += 32) s.D2v[i] = 0.0;
   __syncwarp();
   if (lane < 12) {
-    s.D1v[(6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
-    s.D2v[(6 + lane) * LD + 36 + lane] = h / p[6 + lane % 3];
+    s.D1v[(6 + lane) * LD + 36 + lane] = h * p[24 + lane % 3];
+    s.D2v[(6 + lane) * LD + 36 + lane] = h * p[24 + lane % 3];
   }
   __syncwarp();
 
@@ -216,7 +216,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
             for (int e = 0; e < ND; ++e) Dv[r * LD + gc[e]] = h * ja[k]->d[e] + ((gc[e] == 18 + r) ? 1.0 : 0.0);
           }
           const D2* fo[6] = {&o.Fx, &o.Fy, &o.Fz, &o.Tx, &o.Ty, &o.Tz};
-          const double inv[6] = {1.0 / mass, 1.0 / mass, 1.0 / mass, 1.0 / Ix, 1.0 / Iy, 1.0 / Iz};
+          const double inv[6] = {p[20], p[20], p[20], p[21], p[22], p[23]};
 #pragma unroll
           for (int r = 0; r < 6; ++r) {
 #pragma unroll
@@ -256,11 +256,12 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         const double vnew = xin[18 + li] + h * acc;
         const double w3 = __shfl_sync(full, vnew, 3), w4 = __shfl_sync(full, vnew, 4), w5 = __shfl_sync(full, vnew, 5);
         const double sr = trig[sub][0], cr = trig[sub][1], sp = trig[sub][2], cp = trig[sub][3];
-        const double tp = sp / cp, wyz = sr * w4 + cr * w5;
+        const double icp = 1.0 / cp;
+        const double tp = sp * icp, wyz = sr * w4 + cr * w5;
         double rate = vnew;
         if (lane == 3) rate = w3 + tp * wyz;
         if (lane == 4) rate = cr * w4 - sr * w5;
-        if (lane == 5) rate = wyz / cp;
+        if (lane == 5) rate = wyz * icp;
         if (lane < 18) {
           xout[18 + lane] = vnew;
           xout[lane] = xin[lane] + h * rate;
@@ -272,12 +273,12 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         const int rr = 3 + lane / 2;
         const int cc = (lane == 0) ? 22 : (lane == 1) ? 23 : (lane == 2) ? 23 : (lane == 3) ? 21 : (lane == 4) ? 21 : 22;
         const double w3 = xin[21], w4 = xin[22], w5 = xin[23];
-        const double val = (lane == 0)   ? -h * (Iz - Iy) * w5 / Ix
-                           : (lane == 1) ? -h * (Iz - Iy) * w4 / Ix
-                           : (lane == 2) ? -h * (Ix - Iz) * w3 / Iy
-                           : (lane == 3) ? -h * (Ix - Iz) * w5 / Iy
-                           : (lane == 4) ? -h * (Iy - Ix) * w4 / Iz
-                                         : -h * (Iy - Ix) * w3 / Iz;
+        const double val = (lane == 0)   ? -h * (Iz - Iy) * w5 * p[21]
+                           : (lane == 1) ? -h * (Iz - Iy) * w4 * p[21]
+                           : (lane == 2) ? -h * (Ix - Iz) * w3 * p[22]
+                           : (lane == 3) ? -h * (Ix - Iz) * w5 * p[22]
+                           : (lane == 4) ? -h * (Iy - Ix) * w4 * p[23]
+                                         : -h * (Iy - Ix) * w3 * p[23];
         Dv[rr * LD + cc] += val;
       }
       __syncwarp();
@@ -296,9 +297,9 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
     const double* D1v = s.D1v;
     {
       const double sr = trig[0][0], cr = trig[0][1], sp = trig[0][2], cp = trig[0][3];
-      const double tp = sp / cp, w4 = s.st[1][22], w5 = s.st[1][23];
+      const double icp = 1.0 / cp, tp = sp * icp, w4 = s.st[1][22], w5 = s.st[1][23];
       const double wyz = sr * w4 + cr * w5, wr = cr * w4 - sr * w5;
-      const double N34 = tp * sr, N35 = tp * cr, N44 = cr, N45 = -sr, N54 = sr / cp, N55 = cr / cp;
+      const double N34 = tp * sr, N35 = tp * cr, N44 = cr, N45 = -sr, N54 = sr * icp, N55 = cr * icp;
       // A' = Av + h Aq N1, in place of Av
       for (int idx = lane; idx < 18 * 18; idx += 32) {
         const int r = idx / 18, jc = idx - 18 * r;
@@ -313,8 +314,8 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       if (lane < 18) {
         double* row = s.D2v + lane * LD;
         const double a3 = row[3], a4 = row[4], a5 = row[5];
-        row[3] = a3 * (1.0 + h * tp * wr) + a4 * (-h * wyz) + a5 * (h * wr / cp);
-        row[4] = a3 * (h * wyz / (cp * cp)) + a4 + a5 * (h * wyz * sp / (cp * cp));
+        row[3] = a3 * (1.0 + h * tp * wr) + a4 * (-h * wyz) + a5 * (h * wr * icp);
+        row[4] = a3 * (h * wyz * (icp * icp)) + a4 + a5 * (h * wyz * sp * (icp * icp));
       }
       __syncwarp();
     }
@@ -376,32 +377,37 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
     {
       // rows 3..5: q2 = (I + h M2) D1q + h N2 v2 with the Euler-rate matrices of substep 2
       const double sr = trig[1][0], cr = trig[1][1], sp = trig[1][2], cp = trig[1][3];
-      const double tp = sp / cp, wy = s.st[2][22], wz = s.st[2][23];
+      const double icp = 1.0 / cp, tp = sp * icp, wy = s.st[2][22], wz = s.st[2][23];
       const double wyz = sr * wy + cr * wz, wr = cr * wy - sr * wz;
+      // the step-independent coefficients of the two Euler-rate maps, hoisted out of the column loop
+      const double m33 = 1.0 + h * tp * wr, m34 = h * wyz * (icp * icp), m43 = -h * wyz, m53 = h * wr * icp,
+                   m54 = h * wyz * sp * (icp * icp);
       // D1q rows 3..5 = E1 + h N1 D1v with the Euler-rate matrices of substep 1 
       const double sr1 = trig[0][0], cr1 = trig[0][1], sp1 = trig[0][2], cp1 = trig[0][3];
-      const double tp1 = sp1 / cp1, wy1 = s.st[1][22], wz1 = s.st[1][23];
+      const double icp1 = 1.0 / cp1, tp1 = sp1 * icp1, wy1 = s.st[1][22], wz1 = s.st[1][23];
       const double wyz1 = sr1 * wy1 + cr1 * wz1, wr1 = cr1 * wy1 - sr1 * wz1;
+      const double e33 = 1.0 + h * tp1 * wr1, e34 = h * wyz1 * (icp1 * icp1), e43 = -h * wyz1, e53 = h * wr1 * icp1,
+                   e54 = h * wyz1 * sp1 * (icp1 * icp1);
       for (int c = lane; c < 48; c += 32) {
         const double f3 = D1v[3 * LD + c], f4 = D1v[4 * LD + c], f5 = D1v[5 * LD + c];
         double d3 = h * (f3 + tp1 * (sr1 * f4 + cr1 * f5));
         double d4 = h * (cr1 * f4 - sr1 * f5);
-        double d5 = h * ((sr1 * f4 + cr1 * f5) / cp1);
+        double d5 = h * ((sr1 * f4 + cr1 * f5) * icp1);
         if (c == 3) {
-          d3 += 1.0 + h * tp1 * wr1;
-          d4 += -h * wyz1;
-          d5 += h * wr1 / cp1;
+          d3 += e33;
+          d4 += e43;
+          d5 += e53;
         }
         if (c == 4) {
-          d3 += h * wyz1 / (cp1 * cp1);
+          d3 += e34;
           d4 += 1.0;
-          d5 += h * wyz1 * sp1 / (cp1 * cp1);
+          d5 += e54;
         }
         if (c == 5) d5 += 1.0;
         const double e3 = s.v2s[c], e4 = s.v2s[48 + c], e5 = s.v2s[96 + c];
-        const double q3 = (1.0 + h * tp * wr) * d3 + (h * wyz / (cp * cp)) * d4 + h * (e3 + tp * (sr * e4 + cr * e5));
-        const double q4 = (-h * wyz) * d3 + d4 + h * (cr * e4 - sr * e5);
-        const double q5 = (h * wr / cp) * d3 + (h * wyz * sp / (cp * cp)) * d4 + d5 + h * ((sr * e4 + cr * e5) / cp);
+        const double q3 = m33 * d3 + m34 * d4 + h * (e3 + tp * (sr * e4 + cr * e5));
+        const double q4 = m43 * d3 + d4 + h * (cr * e4 - sr * e5);
+        const double q5 = m53 * d3 + m54 * d4 + d5 + h * ((sr * e4 + cr * e5) * icp);
         if (c < 36) {
           fx[3 * 36 + c] = q3;
           fx[4 * 36 + c] = q4;

@@ -281,20 +281,21 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
         f[k] += __shfl_xor_sync(mask, f[k], 4);
       }
       ROLL_TICK(6);
-      // base accelerations (Quadruped::base_acc): entry k on lane k, one division per lane
-      // (numerator and denominator are selected branch-free)
+      // base accelerations (Quadruped::base_acc): entry k on lane k (numerator and reciprocal
+      // mass / inertia are selected branch-free)
       {
-        const double mass = p[2], Ix = p[3], Iy = p[4], Iz = p[5], grav = p[19];
+        const double Ix = p[3], Iy = p[4], Iz = p[5], grav = p[19];
         const double n3 = f[3] - (Iz - Iy) * vb[4] * vb[5];
         const double n4 = f[4] - (Ix - Iz) * vb[5] * vb[3];
         const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
         const double num = (lane == 0) ? f[0] : (lane == 1) ? f[1] : (lane == 2) ? f[2] : (lane == 3) ? n3 : (lane == 4) ? n4 : n5;
-        const double den = (lane < 3) ? mass : (lane == 3) ? Ix : (lane == 4) ? Iy : Iz;
-        double a = num / den;
+        const double rcp = (lane < 3) ? p[20] : (lane == 3) ? p[21] : (lane == 4) ? p[22] : p[23];
+        double a = num * rcp;
         if (lane == 2) a -= grav;
         if (lane < 6) s.acc[lane] = a;
       }
-      const double tp = B.sp / B.cp;
+      const double icp = 1.0 / B.cp;
+      const double tp = B.sp * icp;
       __syncwarp(mask);
       ROLL_TICK(7);
       // semi-implicit Euler (Quadruped::integrate): v+ first, then q+ = q + h N(q) v+; entries
@@ -316,7 +317,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
           if (k == 0) {
             if (lane == 3) rate = w3 + tp * wyz;
             if (lane == 4) rate = B.cr * w4 - B.sr * w5;
-            if (lane == 5) rate = wyz / B.cp;
+            if (lane == 5) rate = wyz * icp;
           }
           qn[k] = (i < 18) ? (s.x[i] + h * rate) : 0.0;
           fin_step = fin_step && isfinite(qn[k]) && isfinite(vn[k]);

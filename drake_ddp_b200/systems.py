@@ -100,6 +100,9 @@ def quadruped(dt=4e-3, substeps=2, mass=8.252, inertia=(0.07, 0.26, 0.242),
     solve chaotic."""
     p = [dt, float(substeps), mass, *inertia, *joint_inertia, joint_damping, l_abad, l_thigh,
          l_shank, hip_x, hip_y, foot_radius, modulus, mu, v_stiction, g]
+    # masses and inertias enter the model through their reciprocals (csrc/models.h), rounded here once
+    p += [1.0 / mass, *(1.0 / np.asarray(inertia, dtype=np.float64)),
+          *(1.0 / np.asarray(joint_inertia, dtype=np.float64))]
     return AnalyticSystem("quadruped", MODEL_QUADRUPED, 36, 12, np.array(p, dtype=np.float64))
 
 
