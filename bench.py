@@ -382,15 +382,16 @@ def run_b200(args):
 
     # ------------------------------------------------------------------ end-to-end timing
     # Public API with HOST buffers: every step uploads x0 and the control tape from pinned memory,
-    # runs one iteration, and reads the new x0, the new control tape and the costs back; what is
-    # read back is what the next step uploads (closed loop through host memory, like the MPC loops
-    # of the reference's scripts).  HostExchange overlaps the copies with the derivatives +
-    # backward pass where the data is already final.
+    # runs one iteration, and reads the new control tape, x0 and the costs back; what is read back
+    # is what the next step uploads (closed loop through host memory, like the MPC loops of the
+    # reference's scripts).  HostExchange overlaps the copies with the derivatives + backward pass
+    # where the data is already final.  A trajectory that the device re-arms at the end of an
+    # iteration keeps its own (shifted) tape over the stale uploaded row (ddp_apply_staged_inputs).
     x0_pin = torch.from_numpy(x0.copy()).pin_memory()
     u_pin = torch.from_numpy(u0.copy()).pin_memory()
     cost_pin = torch.empty(B, dtype=torch.float64).pin_memory()
     fresh()
-    ex = solver.host_exchange(REPLAN_STEPS)
+    ex = solver.host_exchange()
 
     def e2e_step():
         ex.apply_inputs()
@@ -400,9 +401,8 @@ def run_b200(args):
         ex.wait_controls()
         ex.stage_inputs(x0_pin, u_pin)        # next upload travels under the backward pass
         n_act = solver.iterate_wait()
-        ex.read_rearmed(x0_pin, u_pin)        # re-armed trajectories: new x0, shifted tape rows patched
         gather_costs()
-        solver.get_into(_lib.COST, cost_pin)
+        ex.read_state(x0_pin, cost_pin)       # costs + x0 (the device moves x0 of re-armed trajectories)
         return n_act
 
     ex.stage_inputs(x0_pin, u_pin)
@@ -507,8 +507,8 @@ def run_b200(args):
                                   "linesearch_failed": int((status == 2).sum()),
                                   "resolves_completed": int(resolves.sum())},
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(B * (n + T * m) * 8 + ex.h2d_patch_bytes / max(1, ex.d2h_steps)),
-                    "d2h_bytes_per_step": int(ex.d2h_bytes / max(1, ex.d2h_steps)) + B * 8,
+                    "h2d_bytes_per_step": int(B * (n + T * m) * 8),
+                    "d2h_bytes_per_step": int(ex.d2h_bytes / max(1, ex.d2h_steps)),
                     "ms_per_step": e2e_ms / K, "active_per_step": units_e2e_local / K},
             "gpu_launches": launches_all, "clocks": clocks,
         }

@@ -114,6 +114,7 @@ void carve(Dev& d, double** params, int np, Carver& c) {
   d.acc = c.take<int>(B);
   d.iters = c.take<int>(B);
   d.rearm = c.take<int>(B);
+  d.rearm_mark = c.take<int>(B);
   d.resolves = c.take<int>(B);
   d.L_conv = c.take<double>(B);
   d.mpc_target_adv_buf = c.take<double>(n);
@@ -670,6 +671,18 @@ int ddp_set_mpc_rearm(ddp_solver_t* s, int replan_steps, const double* target_ad
   return 0;
 }
 
+int ddp_apply_staged_inputs(ddp_solver_t* s, const double* x0_dev, const double* u_dev) {
+  GUARD(s);
+  if (!x0_dev || !u_dev) {
+    g_err = "null staging pointer";
+    return DDP_ERR_ARG;
+  }
+  apply_staged_kernel<<<s->d.B, 128, 0, s->stream>>>(s->d, x0_dev, u_dev);
+  s->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int ddp_begin_solve(ddp_solver_t* s) {
   GUARD(s);
   const int B = s->d.B;
@@ -682,6 +695,7 @@ int ddp_begin_solve(ddp_solver_t* s) {
   CK(cudaMemsetAsync(s->d.iters, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.ls_iters, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.rearm, 0, B * 4, s->stream));
+  CK(cudaMemsetAsync(s->d.rearm_mark, 0, B * 4, s->stream));
   CK(cudaMemsetAsync(s->d.resolves, 0, B * 4, s->stream));
   // per-SM CTA-slot bitmasks of the backward sweep: all free between launches; re-zero them in case
   // an earlier launch was aborted with slots taken (they only steer warp roles, never results)

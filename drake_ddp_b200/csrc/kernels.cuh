@@ -31,6 +31,7 @@ struct Dev {
   const double* mpc_target_adv;  // [n] added to x_nom of the trajectory at every resolve (moving target)
   double* mpc_target_adv_buf;
   int *rearm, *resolves;   // [B] flag for mpc_rearm_kernel; resolves finished so far
+  int* rearm_mark;         // [B] re-armed on the device since the last ddp_apply_staged_inputs
   double* L_conv;          // [B] final cost of the last converged solve
   int bwd_flags;  // bit 0: backward_sym_kernel inverts Quu by Gauss-Jordan at every step (no Newton-Schulz)
   int* sm_slots;  // per-SM bitmask of the CTA slots in use (backward_sym_kernel deals warp roles by slot)
@@ -336,7 +337,29 @@ __global__ void mpc_rearm_kernel(Dev d) {
     if (d.mpc_target_adv) xnom[j] += d.mpc_target_adv[j];
   }
   __syncthreads();
-  if (threadIdx.x == 0) d.rearm[b] = 0;
+  if (threadIdx.x == 0) {
+    d.rearm[b] = 0;
+    d.rearm_mark[b] = 1;
+  }
+}
+
+// SetInitialState / SetInitialGuess of an MPC loop that keeps its buffers on the host
+// (mini_cheetah.py:148-149 inside the loop of :190-201), from a staging copy already on the device:
+// x0 <- xs, u_bar <- us, except for the trajectories the device itself re-armed since the last call
+// (their x0 / tape are the newer ones: the staged rows were read back before the shift).
+__global__ void apply_staged_kernel(Dev d, const double* xs, const double* us) {
+  const int b = blockIdx.x;
+  if (d.rearm_mark[b]) {
+    __syncthreads();
+    if (threadIdx.x == 0) d.rearm_mark[b] = 0;
+    return;
+  }
+  const size_t nu = (size_t)d.T * d.m;
+  const double* src = us + (size_t)b * nu;
+  double* dst = d.u_bar + (size_t)b * nu;
+  for (size_t i = threadIdx.x; i < nu; i += blockDim.x) dst[i] = src[i];
+  double* x0 = const_cast<double*>(d.x0) + (size_t)b * d.n;
+  for (int i = threadIdx.x; i < d.n; i += blockDim.x) x0[i] = xs[(size_t)b * d.n + i];
 }
 
 // reset per-iteration line-search state

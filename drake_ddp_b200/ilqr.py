@@ -265,11 +265,8 @@ class BatchedILQR:
         _lib.check(self._L.ddp_iterate_wait(self._h, ctypes.byref(n_active)), "ddp_iterate_wait")
         return n_active.value
 
-    def host_exchange(self, replan_steps=None):
-        ex = HostExchange(self)
-        if replan_steps is not None:
-            ex.replan_steps = int(replan_steps)
-        return ex
+    def host_exchange(self):
+        return HostExchange(self)
 
     def solve(self, max_iters=0) -> int:
         it = ctypes.c_int()
@@ -351,7 +348,8 @@ class HostExchange:
 
         ex.stage_inputs(x0_pinned, u_pinned)      # H2D into a staging buffer, copy stream
         loop:
-            ex.apply_inputs()                     # staging -> x0, u_bar (device copy, solver stream)
+            ex.apply_inputs()                     # staging -> x0, u_bar (device copy, solver stream;
+                                                  # rows the device re-armed itself are kept)
             solver.iterate_linesearch()
             ex.read_controls(u_pinned)            # D2H of u_bar on the copy stream ...
             solver.iterate_finish_async()         # ... under derivatives + backward pass
@@ -378,14 +376,9 @@ class HostExchange:
         self._x0 = solver.device_tensor(_lib.X0)
         self._u = solver.device_tensor(_lib.U_BAR)
         self.ev_applied.record(solver._stream)
-        # re-armed rows (ddp_set_mpc_rearm): host-side shift + patch of the staged upload
-        self.replan_steps = 4
-        self._resolves = np.zeros(solver.B, dtype=np.int32)
-        self._patch_pin = torch.empty((solver.B, solver.T, solver.m), dtype=torch.float64).pin_memory()
-        self._rows_pin = torch.empty(solver.B, dtype=torch.int64).pin_memory()
-        self._patch_dev = torch.empty((solver.B, solver.T, solver.m), dtype=torch.float64, device=dev)
-        self._rows_dev = torch.empty(solver.B, dtype=torch.int64, device=dev)
-        self.d2h_bytes = self.d2h_steps = self.h2d_patch_bytes = 0
+        self._cost = solver.device_tensor(_lib.COST)
+        self.ev_patch = torch.cuda.Event()
+        self.d2h_bytes = self.d2h_steps = 0
 
     def stage_inputs(self, x0_pinned, u_pinned):
         torch = self._torch
@@ -396,13 +389,14 @@ class HostExchange:
             self.ev_staged.record(self.copy_in)
 
     def apply_inputs(self):
-        torch = self._torch
+        """staging -> x0, u_bar on the solver's stream (ddp_apply_staged_inputs: rows the device
+        re-armed itself since the last call keep their newer data)."""
         st = self.s._stream
-        with torch.cuda.stream(st):
-            st.wait_event(self.ev_staged)
-            self._x0.copy_(self.stage_x0, non_blocking=True)
-            self._u.copy_(self.stage_u, non_blocking=True)
-            self.ev_applied.record(st)
+        st.wait_event(self.ev_staged)
+        _lib.check(self.s._L.ddp_apply_staged_inputs(self.s._h, ctypes.c_void_p(self.stage_x0.data_ptr()),
+                                                      ctypes.c_void_p(self.stage_u.data_ptr())),
+                   "ddp_apply_staged_inputs")
+        self.ev_applied.record(st)
 
     def read_controls(self, u_pinned):
         """Call after iterate_linesearch() (u_bar final, solver stream idle)."""
@@ -416,41 +410,17 @@ class HostExchange:
     def wait_controls(self):
         self.ev_read.synchronize()
 
-    def read_rearmed(self, x0_pinned, u_pinned):
-        """With ddp_set_mpc_rearm the device starts the next MPC resolve of every trajectory that
-        converged in this iteration: new x0, shifted tape.  Call after iterate_wait(): reads the
-        resolve counters and x0 back (small), applies the same shift to the re-armed rows of the
-        HOST tape (what the reference's scripts do on the host, mini_cheetah.py:190-198) and patches
-        the staged upload, so host and device keep holding the same closed-loop data."""
+    def read_state(self, x0_pinned, cost_pinned):
+        """x0 (the device moves it when it re-arms a trajectory) and the costs, to host buffers;
+        call after iterate_wait().  Blocks until both have landed."""
         torch = self._torch
-        s = self.s
-        res = s.get_int(_lib.I_RESOLVES)
-        self.ev_staged.synchronize()           # the staged upload has finished reading the pinned buffers
-        s.get_into(_lib.X0, x0_pinned)
-        self.d2h_bytes += res.nbytes + x0_pinned.numel() * 8
-        rows = np.nonzero(res != self._resolves)[0]
-        self._resolves = res
-        with torch.cuda.stream(self.copy_in):
-            self.stage_x0.copy_(x0_pinned, non_blocking=True)
-            self.ev_staged.record(self.copy_in)
-        if rows.size == 0:
-            return 0
-        r = self.replan_steps
-        u = u_pinned.numpy()
-        blk = u[rows]
-        blk[:, :-r] = blk[:, r:].copy()
-        blk[:, -r:] = blk[:, -1:].copy()       # padded with the last control (already moved into place)
-        u[rows] = blk
-        k = rows.size
-        self._patch_pin[:k].copy_(torch.from_numpy(blk))
-        self._rows_pin[:k].copy_(torch.from_numpy(rows.astype(np.int64)))
-        with torch.cuda.stream(self.copy_in):
-            self._patch_dev[:k].copy_(self._patch_pin[:k], non_blocking=True)
-            self._rows_dev[:k].copy_(self._rows_pin[:k], non_blocking=True)
-            self.stage_u.index_copy_(0, self._rows_dev[:k], self._patch_dev[:k])
-            self.ev_staged.record(self.copy_in)
-        self.h2d_patch_bytes += k * (blk.shape[1] * blk.shape[2] * 8 + 8) + x0_pinned.numel() * 8
-        return int(k)
+        st = self.s._stream
+        with torch.cuda.stream(st):
+            x0_pinned.copy_(self._x0, non_blocking=True)
+            cost_pinned.copy_(self._cost, non_blocking=True)
+            self.ev_patch.record(st)
+        self.ev_patch.synchronize()
+        self.d2h_bytes += (x0_pinned.numel() + cost_pinned.numel()) * 8
 
 
 class IterativeLinearQuadraticRegulator:

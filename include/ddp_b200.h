@@ -143,6 +143,13 @@ int ddp_mpc_shift(ddp_solver_t* s, int replan_steps);
  * (default) restores Solve() semantics: converged trajectories stop. */
 int ddp_set_mpc_rearm(ddp_solver_t* s, int replan_steps, const double* target_advance);
 
+/* SetInitialState + SetInitialGuess (ilqr.py:102-109,148-156) of a loop that keeps x0 / u_guess in
+ * host buffers and has already staged them on the device (x0_dev [B][n], u_dev [B][T][m], device
+ * pointers): enqueues the copy on the solver's stream.  Trajectories the device re-armed itself since
+ * the last call (ddp_set_mpc_rearm) keep their newer x0 / tape: the staged rows were read back
+ * before that shift. */
+int ddp_apply_staged_inputs(ddp_solver_t* s, const double* x0_dev, const double* u_dev);
+
 /* Solve(), ilqr.py:669-710, split so the host can print the per-iteration table:
  * ddp_begin_solve sets L = inf, improvement = inf for every trajectory (ilqr.py:681-682);
  * ddp_iterate runs one forward pass + backward pass (ilqr.py:695-697) for every

@@ -425,6 +425,44 @@ def test_split_iterate_and_host_exchange_equal_iterate():
     assert np.array_equal(u_pin.numpy(), ref.get(_lib.U_BAR))
 
 
+def test_host_exchange_with_device_rearm_equals_device_resident_loop():
+    """The end-to-end loop of bench.py (host buffers uploaded and read back every iteration) with the
+    device-side MPC re-arm on: a trajectory the device re-arms keeps its shifted tape over the stale
+    uploaded row (ddp_apply_staged_inputs), so the loop is bit-identical to the device-resident one."""
+    import torch
+    prob = problems.acrobot(40)
+    B, iters = 6, 24
+    x0 = prob.batch_x0(B, seed=5)
+    u0 = np.ascontiguousarray(np.broadcast_to(prob.u_guess.T, (B, prob.N - 1, 1)))
+    ref = make_gpu(prob, B=B, x0=x0, A=4)
+    ref.set_mpc_rearm(2)
+    ref.begin_solve()
+    for _ in range(iters):
+        ref.iterate()
+    assert ref.get_int(_lib.I_RESOLVES).sum() >= B
+    s = make_gpu(prob, B=B, x0=x0, A=4)
+    s.set_mpc_rearm(2)
+    x0_pin = torch.from_numpy(x0.copy()).pin_memory()
+    u_pin = torch.from_numpy(u0.copy()).pin_memory()
+    cost_pin = torch.empty(B, dtype=torch.float64).pin_memory()
+    s.begin_solve()
+    ex = s.host_exchange()
+    ex.stage_inputs(x0_pin, u_pin)
+    for _ in range(iters):
+        ex.apply_inputs()
+        s.iterate_linesearch()
+        ex.read_controls(u_pin)
+        s.iterate_finish_async()
+        ex.wait_controls()
+        ex.stage_inputs(x0_pin, u_pin)
+        s.iterate_wait()
+        ex.read_state(x0_pin, cost_pin)
+    np.testing.assert_array_equal(s.get_int(_lib.I_RESOLVES), ref.get_int(_lib.I_RESOLVES))
+    for which in (_lib.X_BAR, _lib.U_BAR, _lib.K, _lib.COST, _lib.X0, _lib.CONVERGED_COST):
+        assert np.array_equal(s.get(which), ref.get(which)), which
+    assert np.array_equal(cost_pin.numpy(), ref.cost) and np.array_equal(x0_pin.numpy(), ref.get(_lib.X0))
+
+
 def test_quu_regularization_extension_matches_oracle():
     """ddp_set_regularization (SURVEY 8f-4 extension, default 0 = reference): Quu + mu*I in the
     backward pass, against the oracle port with the same mu; mu = 0 stays bit-identical to the
