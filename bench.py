@@ -279,7 +279,7 @@ def dominant(phase_ms, pb, active_per_step, K, ls_mean, hbm_peak, quad=True):
     dom = max(phase_ms, key=phase_ms.get)
     launch_ms = phase_ms[dom] / K
     if dom == "backward":
-        kernel, nbytes = "backward_mma_kernel", pb["backward"] * active_per_step
+        kernel, nbytes = "backward_sym_kernel", pb["backward"] * active_per_step
     elif dom == "derivs":
         kernel, nbytes = ("quad_fused_kernel" if quad else "linearize_kernel"), pb["derivs"] * active_per_step
     else:

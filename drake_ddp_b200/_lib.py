@@ -40,9 +40,10 @@ KP_METHODS = {"setInterval": 0, "adaptiveJerk": 1, "iterativeError": 2}
 TRAJ_RUNNING, TRAJ_CONVERGED, TRAJ_LINESEARCH_FAILED = 0, 1, 2
 
 
-# DMMAs backward_sym_kernel issues per step at (n, m) = (36, 12): the products (8 x 8 tile padding
-# included) + 24 per Newton-Schulz pass, 2.8 passes on average
-BWD_DMMA_PER_STEP_36_12 = 681 + 24 * 2.8
+# DMMAs backward_sym_kernel issues per step at (n, m) = (36, 12): 270 (W = Vxx S) + 189 (upper tiles of
+# S'W) + 30 (K) + 45 (upper tiles of the Vxx update), 8 x 8 tile padding included, + 24 per Newton-
+# Schulz pass, three passes as a rule
+BWD_DMMA_PER_STEP_36_12 = 534 + 24 * 3
 
 
 def is_stale() -> bool:

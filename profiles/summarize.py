@@ -81,12 +81,12 @@ def main():
     tag = sys.argv[1]
     md = [f"# ncu summary `{tag}` (bench.py C4: quadruped n=36 m=12 N=200 B=1024, one B200)", "",
           "Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-          "`python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare shares).", ""]
+          "`python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras` (cold-cache, serialised: compare shares).", ""]
     md += launches(tag) + [""]
     traffic = {}
-    names = {"backward": "backward_mma_kernel", "quad_fused": "quad_fused_kernel", "rollout": "rollout_quad8_kernel",
-             "linearize": "linearize_kernel"}
-    for kern in ("backward", "quad_fused", "linearize", "rollout"):
+    names = {"backward_sym": "backward_sym_kernel", "quad_fused": "quad_fused_kernel",
+             "rollout_quad8": "rollout_quad8_kernel", "linearize": "linearize_kernel"}
+    for kern in ("backward_sym", "quad_fused", "linearize", "rollout_quad8"):
         rep = os.path.join(GO, f"prof_{kern}_{tag}.ncu-rep")
         if not os.path.exists(rep):
             continue
