@@ -543,7 +543,7 @@ def other_configs(torch, problems, hbm_peak):
     """The other BASELINE configs as batch-solve throughput (parity for each is in tests/)."""
     out = {}
     cases = {
-        "C5_arm_ball_n27_N400_B512_setInterval5": (lambda: problems.arm_ball(400), 512, 4),
+        "C5_arm_ball_n27_N400_B512_setInterval5": (lambda: problems.arm_ball(400), 512, None),
         "C4_n37_quat_N200_B1024": (lambda: problems.quadruped_quat(200), 1024, None),
         "C2_acrobot_N40_B50": (lambda: problems.acrobot(40), 50, 8),
         "C3_wall_N200_256_alphas": (lambda: problems.cart_pole_with_wall(200, beta=0.95), 1, 256),

@@ -28,7 +28,7 @@ SYMBOLS = [
     "ddp_iterate", "ddp_iterate_linesearch", "ddp_iterate_finish_async", "ddp_iterate_wait", "ddp_solve",
     "ddp_run_phase", "ddp_get",
     "ddp_put", "ddp_get_int", "ddp_device_ptr", "ddp_array_elems", "ddp_last_timings",
-    "ddp_launch_count", "ddp_peak_fp64", "ddp_mpc_shift", "ddp_set_mpc_rearm", "ddp_apply_staged_inputs",
+    "ddp_launch_count", "ddp_peak_fp64", "ddp_mpc_shift", "ddp_set_mpc_rearm", "ddp_apply_staged_inputs", "ddp_set_control_limits",
 ]
 
 # enums of include/ddp_b200.h
@@ -98,6 +98,7 @@ def lib():
     L.ddp_mpc_shift.argtypes = [c_vp, c_int]
     L.ddp_set_mpc_rearm.argtypes = [c_vp, c_int, c_vp]
     L.ddp_apply_staged_inputs.argtypes = [c_vp, c_vp, c_vp]
+    L.ddp_set_control_limits.argtypes = [c_vp, c_vp, c_vp]
     L.ddp_set_regularization.argtypes = [c_vp, c_dbl]
     L.ddp_iterate.argtypes = [c_vp, ip]
     L.ddp_iterate_linesearch.argtypes = [c_vp]

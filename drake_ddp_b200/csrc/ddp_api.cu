@@ -118,6 +118,7 @@ void carve(Dev& d, double** params, int np, Carver& c) {
   d.resolves = c.take<int>(B);
   d.L_conv = c.take<double>(B);
   d.mpc_target_adv_buf = c.take<double>(n);
+  d.u_lim_buf = c.take<double>(2 * m);
   d.active_save = c.take<int>(B);
   d.status_save = c.take<int>(B);
   d.counters = c.take<int>(4);
@@ -557,6 +558,26 @@ int ddp_set_regularization(ddp_solver_t* s, double quu_reg) {
     return DDP_ERR_ARG;
   }
   s->d.quu_reg = quu_reg;
+  return 0;
+}
+
+int ddp_set_control_limits(ddp_solver_t* s, const double* u_min, const double* u_max) {
+  GUARD(s);
+  const int m = s->d.m;
+  if (!u_min || !u_max) {   // off: the reference's behaviour (SetControlLimits is a no-op there)
+    s->d.u_min = s->d.u_max = nullptr;
+    return 0;
+  }
+  for (int i = 0; i < m; ++i)
+    if (!(u_min[i] <= u_max[i])) {
+      g_err = "u_min must be <= u_max";
+      return DDP_ERR_ARG;
+    }
+  CK(cudaMemcpyAsync(s->d.u_lim_buf, u_min, m * 8, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->d.u_lim_buf + m, u_max, m * 8, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  s->d.u_min = s->d.u_lim_buf;
+  s->d.u_max = s->d.u_lim_buf + m;
   return 0;
 }
 

@@ -18,6 +18,10 @@ struct Dev {
   int n, m, N, T, B, A, n_eps, diag_cost;
   double delta, gamma;
   double quu_reg;  // added to the diagonal of Quu before it is inverted (0: the reference's behaviour)
+  // extension (SetControlLimits is `pass` in the reference, ilqr.py:158-159): when set, the rollout
+  // clamps u_t to [u_min, u_max] ([m] each); nullptr = off = the reference's behaviour
+  const double *u_min, *u_max;
+  double* u_lim_buf;
   const double* params;
   const double *Q, *R, *Qf, *x_nom, *x0, *eps_table;
   double *x_bar, *u_bar, *K, *kappa, *dV, *fx, *fu;
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int pe
 #pragma unroll
         for (int j = 0; j < n; ++j) acc = fma(Kr[j], dx[j], acc);
         acc = ub[r] - eps * kp[r] - acc;
+        if (d.u_min) acc = fmin(fmax(acc, d.u_min[r]), d.u_max[r]);   // extension, off by default
       }
       mine[i] = acc;
     }

@@ -200,7 +200,8 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
         const double other = __shfl_xor_sync(mask, a3[i], 1);
         const double lo = odd ? other : a3[i], hi = odd ? a3[i] : other;   // first half + second half
         const int r = prow + 4 * i;
-        const double u = ub[r] - eps * kp[r] - (lo + hi);
+        double u = ub[r] - eps * kp[r] - (lo + hi);
+        if (d.u_min) u = fmin(fmax(u, d.u_min[r]), d.u_max[r]);   // extension, off by default
         if (!odd) s.u[r] = u;
       }
     }

@@ -140,10 +140,16 @@ class BatchedILQR:
             n_eps += 1
             eps *= self.beta
         if ls_parallel is None:
-            # candidates evaluated speculatively per trajectory in the first line-search round;
-            # the candidate buffer (B*A rollouts) is capped at 2 GiB
+            # Candidates evaluated speculatively per trajectory in the first line-search round.  A
+            # rollout is N-1 dependent steps, so a round costs the same whether it carries one
+            # candidate per trajectory or as many as fit one resident wave of the GPU: take as many
+            # as that (8 for the quadruped kernels: their CTA is 8 candidates of one trajectory, and
+            # 8 resolve > 90 % of the trajectories), within 2 GiB of candidate buffer.
             per_rollout = 8 * (self.N * self.n + self.T * self.m)
-            ls_parallel = max(1, min(8, (2 << 30) // max(1, self.B * per_rollout)))
+            lanes = 1 if (self.n + self.m) <= 8 else (8 if self.system.model_id == 4 else 4)
+            wave = 148 * 2048 // max(1, self.B * lanes)
+            cap = 8 if self.system.model_id == 4 else n_eps
+            ls_parallel = max(1, min(cap, max(8, wave) if cap > 8 else 8, (2 << 30) // max(1, self.B * per_rollout)))
         self.A = max(1, min(int(ls_parallel), n_eps))
         nbytes = L.ddp_workspace_bytes(self.system.model_id, self.N, self.B, self.A)
         assert nbytes > 0, "bad (model, N, B, A)"
@@ -184,6 +190,16 @@ class BatchedILQR:
     def set_regularization(self, quu_reg: float):
         """Extension: Quu + quu_reg*I is inverted in the backward pass (0 = the reference, ilqr.py:654-655)."""
         _lib.check(self._L.ddp_set_regularization(self._h, float(quu_reg)), "ddp_set_regularization")
+
+    def set_control_limits(self, u_min=None, u_max=None):
+        """Extension (the reference's SetControlLimits is `pass`, ilqr.py:158-159): clamp every
+        rollout control to [u_min, u_max]; None switches it off (default = reference behaviour)."""
+        if u_min is None or u_max is None:
+            _lib.check(self._L.ddp_set_control_limits(self._h, None, None), "ddp_set_control_limits")
+            return
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(u_min, dtype=np.float64), (self.m,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(u_max, dtype=np.float64), (self.m,)))
+        _lib.check(self._L.ddp_set_control_limits(self._h, _ptr(lo), _ptr(hi)), "ddp_set_control_limits")
 
     def set_cost(self, Q, R, Qf):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
@@ -468,7 +484,7 @@ class IterativeLinearQuadraticRegulator:
         self._u_guess = u_guess
 
     def SetControlLimits(self, u_min, u_max):
-        pass  # no-op in the reference too (ilqr.py:158-159)
+        pass  # no-op in the reference too (ilqr.py:158-159); BatchedILQR.set_control_limits is the extension
 
     # ---- results in the reference's layouts (time last, ilqr.py:70-83) ---------------------
     @property

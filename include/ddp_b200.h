@@ -117,6 +117,11 @@ int ddp_set_keypoints(ddp_solver_t* s, int method, int minN, int maxN, double je
 /* Extension (no counterpart in the reference, which inverts Quu as is,
  * ilqr.py:654-655): Quu <- Quu + quu_reg * I before the inverse.  Default 0 = reference. */
 int ddp_set_regularization(ddp_solver_t* s, double quu_reg);
+/* SetControlLimits (ilqr.py:158-159) is `pass` in the reference.  Extension: with
+ * u_min, u_max ([m], host pointers) the line-search rollout clamps every control to the box,
+ * u_t = clip(u_bar_t - eps kappa_t - K_t (x_t - x_bar_t)); NULL, NULL (the default) switches it off
+ * and restores the reference's behaviour bit for bit. */
+int ddp_set_control_limits(ddp_solver_t* s, const double* u_min, const double* u_max);
 /* SetRunningCost / SetTerminalCost (ilqr.py:120-146); host pointers, shared by the batch. */
 int ddp_set_cost(ddp_solver_t* s, const double* Q, const double* R, const double* Qf);
 /* SetTargetState (ilqr.py:111-118); x_nom is [n] (per_trajectory=0) or [B][n]. */

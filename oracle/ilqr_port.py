@@ -92,6 +92,7 @@ class IlqrOracle:
         self.N, self.n, self.m = int(num_timesteps), dyn.n, dyn.m
         self.delta, self.beta, self.gamma = delta, beta, gamma
         self.quu_reg = float(quu_reg)   # extension (not in the reference): Quu + quu_reg*I; 0 = ilqr.py:654
+        self.u_lim = None               # extension: (u_min, u_max) box the rollout clamps to; None = reference
         T, n, m = self.N - 1, self.n, self.m
         self.x0 = np.zeros(n)
         self.x_nom = np.zeros(n)
@@ -132,6 +133,8 @@ class IlqrOracle:
         x[0] = self.x0
         for t in range(N - 1):
             u[t] = self.u_bar[t] - eps * self.kappa[t] - self.K[t] @ (x[t] - self.x_bar[t])
+            if self.u_lim is not None:
+                u[t] = np.minimum(np.maximum(u[t], self.u_lim[0]), self.u_lim[1])
             xn = self.dyn.step(x[t], u[t])
             if not np.all(np.isfinite(xn)):      # Drake would throw: ilqr.py:317-323
                 L = np.inf

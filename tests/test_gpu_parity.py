@@ -463,6 +463,75 @@ def test_host_exchange_with_device_rearm_equals_device_resident_loop():
     assert np.array_equal(cost_pin.numpy(), ref.cost) and np.array_equal(x0_pin.numpy(), ref.get(_lib.X0))
 
 
+def test_control_limits_extension_matches_oracle(monkeypatch):
+    """ddp_set_control_limits (SetControlLimits is `pass` in the reference): clamped
+    rollouts against the oracle port with the same box, through the 8-lane quadruped rollout and the
+    generic rollout kernel; switched off again it is bit-identical to a solver that never had limits.
+    (Plain clamping can stall the line search -- then both sides report the reference's
+    "linesearch failed" at the same iteration.)"""
+    lim = 3.2                                     # |u_stand| reaches 3.06: the box binds as soon as the gait starts
+    for mode in ("quad8", "generic"):
+        monkeypatch.delenv("DDP_QUAD_ROLLOUT", raising=False)
+        if mode == "generic":
+            monkeypatch.setenv("DDP_QUAD_ROLLOUT", "generic")
+        prob = problems.quadruped(40)
+        s, o = make_gpu(prob), make_oracle(prob)
+        s.set_control_limits(-lim, lim)
+        o.u_lim = (-lim * np.ones(prob.system.m), lim * np.ones(prob.system.m))
+        s.begin_solve()
+        L = np.inf
+        for _ in range(4):
+            s.iterate()
+            rec = o.iterate(L)
+            L = rec.L
+            assert abs(s.cost[0] - rec.L) <= COST_RTOL * abs(rec.L)
+            assert int(s.get_int(_lib.I_LS_ITERS)[0]) == rec.ls_iters
+            u = s.get(_lib.U_BAR)[0]
+            assert u.max() <= lim and u.min() >= -lim
+            assert np.abs(u - o.u_bar).max() < 1e-8 * max(1.0, np.abs(o.u_bar).max())
+        assert (np.abs(u) == lim).any()                               # the box was active
+    monkeypatch.delenv("DDP_QUAD_ROLLOUT", raising=False)
+    # a clamped pendulum swing-up stalls: same "linesearch failed" on both sides, same iteration
+    prob = problems.pendulum(60)
+    s, o = make_gpu(prob), make_oracle(prob)
+    s.set_control_limits(-2.0, 2.0)
+    o.u_lim = (-2.0 * np.ones(1), 2.0 * np.ones(1))
+    with pytest.raises(RuntimeError, match="linesearch failed"):
+        o.solve(max_iters=10)
+    s.solve(max_iters=10)
+    assert s.status[0] == _lib.TRAJ_LINESEARCH_FAILED and s.get_int(_lib.I_ITERS)[0] in (len(o.trace), len(o.trace) + 1)
+    assert abs(s.cost[0] - o.trace[-1].L) <= COST_RTOL * abs(o.trace[-1].L)
+    prob = problems.quadruped(40)
+    s2, ref = make_gpu(prob), make_gpu(prob)
+    s2.set_control_limits(-lim, lim)
+    s2.set_control_limits(None, None)
+    for z in (s2, ref):
+        z.begin_solve()
+        for _ in range(3):
+            z.iterate()
+    assert np.array_equal(s2.get(_lib.U_BAR), ref.get(_lib.U_BAR)) and np.array_equal(s2.cost, ref.cost)
+
+
+def test_compute_sanitizer_clean_on_a_whole_iteration():
+    """compute-sanitizer memcheck / racecheck / synccheck on two full iLQR iterations (rollout,
+    fused linearization, symmetric backward sweep with its mbarrier / named-barrier dataflow) of
+    small quadruped and quadruped_quat problems: 0 errors."""
+    import shutil
+    import subprocess
+    import sys
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tool in ("memcheck", "racecheck", "synccheck"):
+        r = subprocess.run([exe, "--tool", tool, "--error-exitcode", "7", sys.executable,
+                            os.path.join(root, "tests", "sanitize_small.py")],
+                           capture_output=True, text=True, timeout=900, cwd=root)
+        tail = (r.stdout + r.stderr)[-1500:]
+        assert r.returncode == 0, (tool, tail)
+        assert "ERROR SUMMARY: 0 errors" in r.stdout + r.stderr or "RACECHECK SUMMARY: 0 hazards" in r.stdout + r.stderr, (tool, tail)
+
+
 def test_quu_regularization_extension_matches_oracle():
     """ddp_set_regularization (SURVEY 8f-4 extension, default 0 = reference): Quu + mu*I in the
     backward pass, against the oracle port with the same mu; mu = 0 stays bit-identical to the
