@@ -64,6 +64,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+# Test-only build for compute-sanitizer's synccheck / racecheck: the same sources with the
+# intra-CTA hand-offs of backward_sym_kernel as non-aligned named barriers instead of aligned
+# ones + mbarriers (csrc/backward_sym.cuh, DDP_SANITIZER_BUILD, says why).  Never loaded by the
+# product: only tests/test_gpu_parity.py points DDP_B200_LIB at it for those two passes.
+RACECHECK_LIB_PATH = os.path.join(_HERE, "libddp_b200_racecheck.so")
+
+
+def build_racecheck(force: bool = False) -> str:
+    if not force and os.path.exists(RACECHECK_LIB_PATH):
+        t = os.path.getmtime(RACECHECK_LIB_PATH)
+        if not any(os.path.exists(d) and os.path.getmtime(d) > t for d in _DEPS):
+            return RACECHECK_LIB_PATH
+    tmp = RACECHECK_LIB_PATH + f".{os.getpid()}.tmp"
+    subprocess.check_call(["nvcc"] + NVCC_FLAGS + ["-DDDP_SANITIZER_BUILD"] + _SOURCES + ["-o", tmp])
+    os.replace(tmp, RACECHECK_LIB_PATH)
+    return RACECHECK_LIB_PATH
+
+
 _lib = None
 
 
