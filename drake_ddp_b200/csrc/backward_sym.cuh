@@ -96,6 +96,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 //    warp arrives when ITS part is done and only waits where it needs the others; the sanitizer
 //    build does them with bar.sync / bar.arrive at the wait points (stricter: a wait becomes a
 //    rendezvous), everything else is the same code.
+#ifndef DDP_BWD_BARQ_NAMED
+#define DDP_BWD_BARQ_NAMED 0
+#endif
+constexpr bool kBsBarQNamed = DDP_BWD_BARQ_NAMED != 0;   // experiment: "Q-terms complete" as bar.sync instead of an mbarrier
 #ifdef DDP_SANITIZER_BUILD
 constexpr bool kBsNamed = true;
 #define DDP_BAR_SYNC "barrier.sync"
@@ -576,7 +580,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
     // ---- all Q-terms complete and Quu^-1 ready ---------------------------------------------------
     __syncwarp();
     BS_TICK(7);
-    if (kBsNamed) named_bar_sync(4, NT);
+    if (kBsNamed || kBsBarQNamed) named_bar_sync(4, NT);
     else {
       if (x.lane == 0) mbar_arrive(&s.barQ);
       mbar_wait(&s.barQ, parityQ);
@@ -798,7 +802,7 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
       invert_warp<m>(s.Quu, s.QuuInv);
     __syncwarp();
     BS_TICK(5);
-    if (kBsNamed) named_bar_sync(4, NT);
+    if (kBsNamed || kBsBarQNamed) named_bar_sync(4, NT);
     else {
       if (lane == 0) mbar_arrive(&s.barQ);
       mbar_wait(&s.barQ, parityQ);   // ... and all Q-terms complete

@@ -200,14 +200,22 @@ int launch_backward(ddp_solver* s) {
   return 0;
 }
 
+template <bool QUAT>
+void launch_rollout_quad8(ddp_solver* s, int ls_base, int per_traj, int n_items) {
+  if (ls_base == 0 && per_traj == kRqCands && n_items == s->d.B * kRqCands)
+    rollout_quad8_kernel<true, QUAT><<<s->d.B, kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+  else
+    rollout_quad8_kernel<false, QUAT><<<cdiv(n_items, kRqCands), kRqLanes * kRqCands, 0, s->stream>>>(
+        s->d, ls_base, per_traj, n_items);
+  s->launches++;
+}
 int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
-  if (s->model == MODEL_QUADRUPED && s->quad_rollout8) {
-    if (ls_base == 0 && per_traj == kRqCands && n_items == s->d.B * kRqCands)
-      rollout_quad8_kernel<true><<<s->d.B, kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
-    else
-      rollout_quad8_kernel<false><<<cdiv(n_items, kRqCands), kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base,
-                                                                                                  per_traj, n_items);
-    s->launches++;
+  if (s->quad_rollout8 && s->model == MODEL_QUADRUPED) {
+    launch_rollout_quad8<false>(s, ls_base, per_traj, n_items);
+    return 0;
+  }
+  if (s->quad_rollout8 && s->model == MODEL_QUADRUPED_QUAT) {   // the reference's n = 37 layout
+    launch_rollout_quad8<true>(s, ls_base, per_traj, n_items);
     return 0;
   }
   DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base, per_traj, n_items));

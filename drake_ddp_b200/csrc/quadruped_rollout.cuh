@@ -17,6 +17,13 @@
 // The state lives in shared memory (36 doubles per candidate).  Values equal
 // Quadruped::step<double>() up to the association of the feedback sum; costs are summed per
 // lane and combined once at the end.
+//
+// QUAT = true is the same kernel for QuadrupedQuat, the reference's own state layout
+// (mini_cheetah.py:41-57, n = 37: q = [quat, pos, joints], v = [w_world, v_lin, joint rates]): the
+// legs, the butterfly, the feedback split (19 + 18 columns) and the cost are shared; only the base
+// differs -- rotation from the normalised quaternion instead of three sines / cosines, the
+// angular velocity taken to the body frame for the legs and Euler's equations, the angular
+// acceleration taken back to the world frame, and the quaternion rate instead of Euler rates.
 #pragma once
 #include "kernels.cuh"
 
@@ -26,14 +33,32 @@ constexpr int kRqLanes = 8;        // lanes per candidate
 constexpr int kRqCands = 8;        // candidates per CTA (64 threads)
 
 struct RqCandSmem {
-  double x[36];     // current state
+  double x[38];     // current state (36 or 37 entries)
   double vn[18];    // staged v+ of the substep
   double acc[18];   // accelerations of the substep
   double u[12];     // controls of the step
 };
 
+// state layout of the two base parameterisations and the layout of one staged step
+template <bool QUAT>
+struct RqLayout {
+  static constexpr int n = QUAT ? 37 : 36;
+  static constexpr int NQ = QUAT ? 19 : 18;   // first velocity entry
+  static constexpr int JQ = QUAT ? 7 : 6;     // first joint angle
+  static constexpr int JV = NQ + 6;           // first joint rate
+  static constexpr int PZ = QUAT ? 6 : 2;     // base height
+  static constexpr int HL = (n + 1) / 2;      // columns of the first half of a feedback row (18 / 19)
+  // staged operands of one step (doubles): K_t | x_bar_t (padded to even) | u_bar_t | kappa_t
+  static constexpr int XB = 12 * n, UB = XB + ((n + 1) & ~1), KP = UB + 12, STAGE = KP + 12;
+};
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gmem_src)
                : "memory");
 }
@@ -42,7 +67,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 // one trajectory, so its per-step operands (K_t, x_bar_t, u_bar_t, kappa_t: 3936 bytes) are
 // staged once per warp (4 candidates) into a double buffer with cp.async, one step ahead,
 // instead of being fetched by every candidate through L1.
-constexpr int kRqStage = 432 + 36 + 12 + 12;   // doubles per staged step
 
 #ifdef DDP_ROLL_PROFILE
 __device__ long long g_roll_prof[16];
@@ -58,11 +82,13 @@ __device__ long long g_roll_prof[16];
 #define ROLL_TICK(i)
 #endif
 
-template <bool SHARED>
+template <bool SHARED, bool QUAT>
 __global__ void __launch_bounds__(kRqLanes * kRqCands, 7)
 rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   typedef Quadruped Qd;
-  constexpr int n = 36, m = 12;
+  typedef RqLayout<QUAT> Ly;
+  constexpr int n = Ly::n, m = 12, NQ = Ly::NQ, JQ = Ly::JQ, JV = Ly::JV, HL = Ly::HL;
+  constexpr int kRqStage = Ly::STAGE;
   __shared__ RqCandSmem sm[kRqCands];
   // [warp][buffer][operands of one step]: every warp (4 candidates) keeps its own copy, so only
   // warp-level synchronisation is needed
@@ -126,11 +152,21 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   auto stage = [&](int t, int buf) {   // SHARED: all threads of the warp
     char* dst = reinterpret_cast<char*>(stage_buf[buf]);
     const char* gK = reinterpret_cast<const char*>(d.K + ((size_t)b * d.T + t) * m * n);
-    for (int ch = wl; ch < 216; ch += 32) cp_async16(dst + 16 * ch, gK + 16 * ch);
+    for (int ch = wl; ch < 6 * n; ch += 32) cp_async16(dst + 16 * ch, gK + 16 * ch);
+    const char* gx = reinterpret_cast<const char*>(d.x_bar + ((size_t)b * d.N + t) * n);
+    const char* gu = reinterpret_cast<const char*>(d.u_bar + ((size_t)b * d.T + t) * m);
+    const char* gk = reinterpret_cast<const char*>(d.kappa + ((size_t)b * d.T + t) * m);
     const int q = wl;
-    if (q < 18) cp_async16(dst + 3456 + 16 * q, reinterpret_cast<const char*>(d.x_bar + ((size_t)b * d.N + t) * n) + 16 * q);
-    else if (q < 24) cp_async16(dst + 3744 + 16 * (q - 18), reinterpret_cast<const char*>(d.u_bar + ((size_t)b * d.T + t) * m) + 16 * (q - 18));
-    else if (q < 30) cp_async16(dst + 3840 + 16 * (q - 24), reinterpret_cast<const char*>(d.kappa + ((size_t)b * d.T + t) * m) + 16 * (q - 24));
+    if (!QUAT) {
+      if (q < 18) cp_async16(dst + 8 * Ly::XB + 16 * q, gx + 16 * q);
+      else if (q < 24) cp_async16(dst + 8 * Ly::UB + 16 * (q - 18), gu + 16 * (q - 18));
+      else if (q < 30) cp_async16(dst + 8 * Ly::KP + 16 * (q - 24), gk + 16 * (q - 24));
+    } else {
+      // a 37-entry state row starts 16-byte aligned only at every other step: 8-byte copies
+      for (int ch = q; ch < n; ch += 32) cp_async8(dst + 8 * (Ly::XB + ch), gx + 8 * ch);
+      if (q >= 8 && q < 14) cp_async16(dst + 8 * Ly::UB + 16 * (q - 8), gu + 16 * (q - 8));
+      else if (q >= 14 && q < 20) cp_async16(dst + 8 * Ly::KP + 16 * (q - 14), gk + 16 * (q - 14));
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (SHARED) stage(0, 0);
@@ -166,32 +202,40 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
     }
     ROLL_TICK(1);
     const double* Kt = SHARED ? stage_buf[t & 1] : d.K + ((size_t)b * T + t) * m * n;
-    const double* xb = SHARED ? stage_buf[t & 1] + 432 : d.x_bar + ((size_t)b * N + t) * n;
-    const double* ub = SHARED ? stage_buf[t & 1] + 468 : d.u_bar + ((size_t)b * T + t) * m;
-    const double* kp = SHARED ? stage_buf[t & 1] + 480 : d.kappa + ((size_t)b * T + t) * m;
+    const double* xb = SHARED ? stage_buf[t & 1] + Ly::XB : d.x_bar + ((size_t)b * N + t) * n;
+    const double* ub = SHARED ? stage_buf[t & 1] + Ly::UB : d.u_bar + ((size_t)b * T + t) * m;
+    const double* kp = SHARED ? stage_buf[t & 1] + Ly::KP : d.kappa + ((size_t)b * T + t) * m;
     const double dv_t = d.dV[(size_t)b * T + t];   // issued early, consumed at the end of the step
     if (!SHARED && t + 1 < T) {   // pull the next step's gain half-rows towards L1 while this step computes
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const char* pr = reinterpret_cast<const char*>(Kt + (size_t)m * n + (size_t)(prow + 4 * i) * n + 18 * hh);
+        const char* pr = reinterpret_cast<const char*>(Kt + (size_t)m * n + (size_t)(prow + 4 * i) * n + HL * hh);
         asm volatile("prefetch.global.L1 [%0];" ::"l"(pr));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128));
       }
     }
     // ---- u_t = u_bar_t - eps*kappa_t - K_t (x_t - x_bar_t)            (ilqr.py:313) ----------
     {
-      double dx[18];
+      // this lane's half of the columns: [HL * hh, HL * hh + HL), clipped to n (19 + 18 at n = 37)
+      double dx[HL];
 #pragma unroll
-      for (int j = 0; j < 18; ++j) dx[j] = s.x[18 * hh + j] - xb[18 * hh + j];
+      for (int j = 0; j < HL; ++j) {
+        const bool in = (2 * HL == n) || (HL * hh + j < n);
+        dx[j] = in ? (s.x[HL * hh + j] - xb[HL * hh + j]) : 0.0;
+      }
       double a3[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const double* Kr = Kt + (size_t)(prow + 4 * i) * n + 18 * hh;
+        const double* Kr = Kt + (size_t)(prow + 4 * i) * n + HL * hh;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 18; j += 2) {
-          a0 = fma(Kr[j], dx[j], a0);
-          a1 = fma(Kr[j + 1], dx[j + 1], a1);
+        for (int j = 0; j < HL; j += 2) {
+          const bool in0 = (2 * HL == n) || (HL * hh + j < n);
+          a0 = fma(in0 ? Kr[j] : 0.0, dx[j], a0);
+          if (j + 1 < HL) {
+            const bool in1 = (2 * HL == n) || (HL * hh + j + 1 < n);
+            a1 = fma(in1 ? Kr[j + 1] : 0.0, dx[j + 1], a1);
+          }
         }
         a3[i] = a0 + a1;
       }
@@ -246,29 +290,46 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
     bool fin_step = true;
     for (int it = 0; it < sub_n; ++it) {
       // two sincos per lane: even lane of leg l: abad, hip + knee; odd lane: hip, one base angle
-      const double qh_ = s.x[7 + 3 * leg];
-      const double ang1 = odd ? qh_ : s.x[6 + 3 * leg];
-      const double ang2 = odd ? s.x[3 + (leg < 3 ? leg : 0)] : (qh_ + s.x[8 + 3 * leg]);
+      // (QUAT: no base angles; the odd lanes' second pair is not used)
+      const double qh_ = s.x[JQ + 1 + 3 * leg];
+      const double ang1 = odd ? qh_ : s.x[JQ + 3 * leg];
+      const double ang2 = (!QUAT && odd) ? s.x[3 + (leg < 3 ? leg : 0)] : (qh_ + s.x[JQ + 2 + 3 * leg]);
       double s1, c1, s2, c2;
       sincos_(ang1, &s1, &c1);
       sincos_(ang2, &s2, &c2);
       ROLL_TICK(4);
       Qd::BasePose<double> B;
-      B.sr = __shfl_sync(mask, s2, gbase + 1);
-      B.cr = __shfl_sync(mask, c2, gbase + 1);
-      B.sp = __shfl_sync(mask, s2, gbase + 3);
-      B.cp = __shfl_sync(mask, c2, gbase + 3);
-      const double sy = __shfl_sync(mask, s2, gbase + 5), cy = __shfl_sync(mask, c2, gbase + 5);
-      Qd::base_pose_trig(sy, cy, B);
+      double vb[6];   // [world linear velocity | body angular velocity]: what the legs want
+      if (!QUAT) {
+        B.sr = __shfl_sync(mask, s2, gbase + 1);
+        B.cr = __shfl_sync(mask, c2, gbase + 1);
+        B.sp = __shfl_sync(mask, s2, gbase + 3);
+        B.cp = __shfl_sync(mask, c2, gbase + 3);
+        const double sy = __shfl_sync(mask, s2, gbase + 5), cy = __shfl_sync(mask, c2, gbase + 5);
+        Qd::base_pose_trig(sy, cy, B);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vb[k] = s.x[18 + k];
+      } else {
+        // rotation matrix of the normalised quaternion (QuadrupedQuat::step), every lane
+        const double q0 = s.x[0], q1 = s.x[1], q2 = s.x[2], q3 = s.x[3];
+        const double inn = 1.0 / sqrt_(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        const double a = q0 * inn, b_ = q1 * inn, c_ = q2 * inn, d_ = q3 * inn;
+        B.R00 = 1.0 - 2.0 * (c_ * c_ + d_ * d_); B.R01 = 2.0 * (b_ * c_ - a * d_); B.R02 = 2.0 * (b_ * d_ + a * c_);
+        B.R10 = 2.0 * (b_ * c_ + a * d_); B.R11 = 1.0 - 2.0 * (b_ * b_ + d_ * d_); B.R12 = 2.0 * (c_ * d_ - a * b_);
+        B.R20 = 2.0 * (b_ * d_ - a * c_); B.R21 = 2.0 * (c_ * d_ + a * b_); B.R22 = 1.0 - 2.0 * (b_ * b_ + c_ * c_);
+        B.sr = 0.0; B.cr = 1.0; B.sp = 0.0; B.cp = 1.0;
+        const double w0 = s.x[19], w1 = s.x[20], w2 = s.x[21];
+        vb[0] = s.x[22]; vb[1] = s.x[23]; vb[2] = s.x[24];
+        vb[3] = B.R00 * w0 + B.R10 * w1 + B.R20 * w2;
+        vb[4] = B.R01 * w0 + B.R11 * w1 + B.R21 * w2;
+        vb[5] = B.R02 * w0 + B.R12 * w1 + B.R22 * w2;
+      }
       const double sh = __shfl_sync(mask, s1, wl | 1), ch = __shfl_sync(mask, c1, wl | 1);
       double f[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      double vb[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) vb[k] = s.x[18 + k];
       if (!odd) {
         Qd::LegOut<double> o;
-        Qd::leg_trig(sx, sd, s1, c1, sh, ch, s2, c2, s.x[24 + 3 * leg], s.x[25 + 3 * leg], s.x[26 + 3 * leg], ua, uh, uk,
-                     s.x[2], vb, B, p, o);
+        Qd::leg_trig(sx, sd, s1, c1, sh, ch, s2, c2, s.x[JV + 3 * leg], s.x[JV + 1 + 3 * leg], s.x[JV + 2 + 3 * leg], ua, uh,
+                     uk, s.x[Ly::PZ], vb, B, p, o);
         f[0] = o.Fx; f[1] = o.Fy; f[2] = o.Fz; f[3] = o.Tx; f[4] = o.Ty; f[5] = o.Tz;
         s.acc[6 + 3 * leg] = o.a0;
         s.acc[7 + 3 * leg] = o.a1;
@@ -282,54 +343,94 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
         f[k] += __shfl_xor_sync(mask, f[k], 4);
       }
       ROLL_TICK(6);
-      // base accelerations (Quadruped::base_acc): entry k on lane k (numerator and reciprocal
-      // mass / inertia are selected branch-free)
-      {
-        const double Ix = p[3], Iy = p[4], Iz = p[5], grav = p[19];
-        const double n3 = f[3] - (Iz - Iy) * vb[4] * vb[5];
-        const double n4 = f[4] - (Ix - Iz) * vb[5] * vb[3];
-        const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
+      // base accelerations: entry k on lane k (numerator and reciprocal mass / inertia are selected
+      // branch-free)
+      const double Ix = p[3], Iy = p[4], Iz = p[5], grav = p[19];
+      const double n3 = f[3] - (Iz - Iy) * vb[4] * vb[5];
+      const double n4 = f[4] - (Ix - Iz) * vb[5] * vb[3];
+      const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
+      double icp = 1.0, tp = 0.0;
+      if (!QUAT) {   // Quadruped::base_acc: [linear | body angular]
         const double num = (lane == 0) ? f[0] : (lane == 1) ? f[1] : (lane == 2) ? f[2] : (lane == 3) ? n3 : (lane == 4) ? n4 : n5;
         const double rcp = (lane < 3) ? p[20] : (lane == 3) ? p[21] : (lane == 4) ? p[22] : p[23];
         double a = num * rcp;
         if (lane == 2) a -= grav;
         if (lane < 6) s.acc[lane] = a;
+        icp = 1.0 / B.cp;
+        tp = B.sp * icp;
+      } else {       // QuadrupedQuat::step: [world angular = R (body angular) | linear]
+        const double ab0 = n3 * p[21], ab1 = n4 * p[22], ab2 = n5 * p[23];
+        const double r0 = (lane == 0) ? B.R00 : (lane == 1) ? B.R10 : B.R20;
+        const double r1 = (lane == 0) ? B.R01 : (lane == 1) ? B.R11 : B.R21;
+        const double r2 = (lane == 0) ? B.R02 : (lane == 1) ? B.R12 : B.R22;
+        const double arot = r0 * ab0 + r1 * ab1 + r2 * ab2;
+        double alin = ((lane == 3) ? f[0] : (lane == 4) ? f[1] : f[2]) * p[20];
+        if (lane == 5) alin -= grav;
+        if (lane < 6) s.acc[lane] = (lane < 3) ? arot : alin;
       }
-      const double icp = 1.0 / B.cp;
-      const double tp = B.sp * icp;
       __syncwarp(mask);
       ROLL_TICK(7);
-      // semi-implicit Euler (Quadruped::integrate): v+ first, then q+ = q + h N(q) v+; entries
-      // lane, lane + 8, lane + 16; the Euler-rate rows 3..5 get v+ of 3..5 by shuffle
+      // semi-implicit Euler: v+ first, then q+ = q + h N(q) v+; velocity entries lane, lane + 8,
+      // lane + 16; the base attitude rows get the new angular velocity by shuffle
       {
         double vn[3], qn[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int i = lane + kRqLanes * k;
-          vn[k] = (i < 18) ? (s.x[18 + i] + h * s.acc[i]) : 0.0;
+          vn[k] = (i < 18) ? (s.x[NQ + i] + h * s.acc[i]) : 0.0;
         }
-        const double w3 = __shfl_sync(mask, vn[0], gbase + 3), w4 = __shfl_sync(mask, vn[0], gbase + 4),
-                     w5 = __shfl_sync(mask, vn[0], gbase + 5);
-        const double wyz = B.sr * w4 + B.cr * w5;
+        if (!QUAT) {
+          const double w3 = __shfl_sync(mask, vn[0], gbase + 3), w4 = __shfl_sync(mask, vn[0], gbase + 4),
+                       w5 = __shfl_sync(mask, vn[0], gbase + 5);
+          const double wyz = B.sr * w4 + B.cr * w5;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int i = lane + kRqLanes * k;
-          double rate = vn[k];
-          if (k == 0) {
-            if (lane == 3) rate = w3 + tp * wyz;
-            if (lane == 4) rate = B.cr * w4 - B.sr * w5;
-            if (lane == 5) rate = wyz * icp;
+          for (int k = 0; k < 3; ++k) {
+            const int i = lane + kRqLanes * k;
+            double rate = vn[k];
+            if (k == 0) {
+              if (lane == 3) rate = w3 + tp * wyz;
+              if (lane == 4) rate = B.cr * w4 - B.sr * w5;
+              if (lane == 5) rate = wyz * icp;
+            }
+            qn[k] = (i < 18) ? (s.x[i] + h * rate) : 0.0;
+            fin_step = fin_step && isfinite(qn[k]) && isfinite(vn[k]);
           }
-          qn[k] = (i < 18) ? (s.x[i] + h * rate) : 0.0;
-          fin_step = fin_step && isfinite(qn[k]) && isfinite(vn[k]);
-        }
-        __syncwarp(mask);   // every read of the old state done
+          __syncwarp(mask);   // every read of the old state done
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int i = lane + kRqLanes * k;
-          if (i < 18) {
-            s.x[i] = qn[k];
-            s.x[18 + i] = vn[k];
+          for (int k = 0; k < 3; ++k) {
+            const int i = lane + kRqLanes * k;
+            if (i < 18) {
+              s.x[i] = qn[k];
+              s.x[18 + i] = vn[k];
+            }
+          }
+        } else {
+          // qdot = 0.5 (0, w_W) (x) q with the NEW angular velocity; quaternion entry e on lane e
+          const double w0 = __shfl_sync(mask, vn[0], gbase + 0), w1 = __shfl_sync(mask, vn[0], gbase + 1),
+                       w2 = __shfl_sync(mask, vn[0], gbase + 2);
+          const double q0 = s.x[0], q1 = s.x[1], q2 = s.x[2], q3 = s.x[3];
+          const double e0 = q0 + (0.5 * h) * (-(w0 * q1) - w1 * q2 - w2 * q3);
+          const double e1 = q1 + (0.5 * h) * (w0 * q0 + w1 * q3 - w2 * q2);
+          const double e2 = q2 + (0.5 * h) * (w1 * q0 + w2 * q1 - w0 * q3);
+          const double e3 = q3 + (0.5 * h) * (w2 * q0 + w0 * q2 - w1 * q1);
+          const double qe = (lane == 0) ? e0 : (lane == 1) ? e1 : (lane == 2) ? e2 : e3;
+          if (lane < 4) fin_step = fin_step && isfinite(qe);
+          // position / joint entry that goes with velocity entry i >= 3: q index i + 1
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int i = lane + kRqLanes * k;
+            qn[k] = (i >= 3 && i < 18) ? (s.x[i + 1] + h * vn[k]) : 0.0;
+            fin_step = fin_step && isfinite(qn[k]) && isfinite(vn[k]);
+          }
+          __syncwarp(mask);   // every read of the old state done
+          if (lane < 4) s.x[lane] = qe;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int i = lane + kRqLanes * k;
+            if (i < 18) {
+              s.x[NQ + i] = vn[k];
+              if (i >= 3) s.x[i + 1] = qn[k];
+            }
           }
         }
       }

@@ -146,9 +146,10 @@ class BatchedILQR:
             # as that (8 for the quadruped kernels: their CTA is 8 candidates of one trajectory, and
             # 8 resolve > 90 % of the trajectories), within 2 GiB of candidate buffer.
             per_rollout = 8 * (self.N * self.n + self.T * self.m)
-            lanes = 1 if (self.n + self.m) <= 8 else (8 if self.system.model_id == 4 else 4)
+            quad = self.system.model_id in (4, 6)       # quadruped, quadruped_quat: the 8-lane rollout
+            lanes = 1 if (self.n + self.m) <= 8 else (8 if quad else 4)
             wave = 148 * 2048 // max(1, self.B * lanes)
-            cap = 8 if self.system.model_id == 4 else n_eps
+            cap = 8 if quad else n_eps
             ls_parallel = max(1, min(cap, max(8, wave) if cap > 8 else 8, (2 << 30) // max(1, self.B * per_rollout)))
         self.A = max(1, min(int(ls_parallel), n_eps))
         nbytes = L.ddp_workspace_bytes(self.system.model_id, self.N, self.B, self.A)

@@ -63,12 +63,17 @@ if os.environ.get("PB_PROF"):
     _lib.lib().ddp_debug_bwd_profile(buf)
     print('gauss-jordan fallbacks (all launches):', buf[127], 'of', B * (N - 1), 'per launch; newton passes (all launches):', buf[126])
     a = np.array(buf[:], dtype=np.int64).reshape(2, 4, 16)[:, :, :11]
-    names = ["loop", "mbar", "A1+bar|lxlu", "A2|waitQuu", "A3+bar|inv", "B", "S1", "C1", "bar1", "C2|vecC", "S2"]
+    # prof_acc[i] = cycles between the previous tick and BS_TICK(i) (backward_sym.cuh)
+    dn = ["loop", "wait fx/fu", "bar0", "W other strips", "W fu strips + Quu tiles", "M tiles (2b)", "wait barV",
+          "route stores", "wait barQ", "K + update"]
+    vn = ["loop", "wait fx/fu", "bar0", "lx lu", "wait Quu (bar2)", "inverse", "wait barQ", "Qx Qu + wait barS",
+          "kappa dV Vx"]
     for cta in range(2):
         for w in range(4):
+            nm_ = dn if w < 3 else vn
             tot = a[cta, w].sum()
             print("cta", cta, f"dmma role {w}" if w < 3 else "vector warp", "cycles/step", int(tot / (N - 1)),
-                  {nm: int(v / (N - 1)) for nm, v in zip(names, a[cta, w])})
+                  {nm: int(v / (N - 1)) for nm, v in zip(nm_, a[cta, w])})
 
 if os.environ.get("PB_ROLLPROF"):
     import ctypes

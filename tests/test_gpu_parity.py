@@ -366,10 +366,12 @@ def test_backward_newton_schulz_inverse_matches_gauss_jordan(monkeypatch):
         assert relerr(a, b_) < 1e-10
 
 
-def test_quadruped_rollout8_matches_generic_rollout(monkeypatch):
-    """The 8-lane quadruped rollout (csrc/quadruped_rollout.cuh) against the generic rollout kernel:
-    same candidates, same accepted step, states equal up to the association of the feedback sum."""
-    prob = problems.quadruped(60)
+@pytest.mark.parametrize("name", ["quadruped", "quadruped_quat"])
+def test_quadruped_rollout8_matches_generic_rollout(monkeypatch, name):
+    """The 8-lane quadruped rollout (csrc/quadruped_rollout.cuh; QUAT = the reference's n = 37
+    layout) against the generic rollout kernel: same candidates, same accepted step, states equal
+    up to the association of the feedback sum."""
+    prob = getattr(problems, name)(60)
     B = 6
     x0 = prob.batch_x0(B, seed=2)
     out = {}
@@ -377,19 +379,22 @@ def test_quadruped_rollout8_matches_generic_rollout(monkeypatch):
         monkeypatch.delenv("DDP_QUAD_ROLLOUT", raising=False)
         if mode == "generic":
             monkeypatch.setenv("DDP_QUAD_ROLLOUT", "generic")
-        s = make_gpu(prob, B=B, x0=x0, A=4)
-        s.begin_solve()
-        for _ in range(3):
-            s.iterate()
-        out[mode] = (s.get(_lib.X_BAR), s.get(_lib.U_BAR), s.cost.copy(), s.get_int(_lib.I_LS_ITERS).copy(),
-                     s.get(_lib.CAND_COST).copy())
-    assert np.array_equal(out["quad8"][3], out["generic"][3])
-    assert relerr(out["quad8"][0], out["generic"][0]) < 1e-10
-    assert relerr(out["quad8"][1], out["generic"][1]) < 1e-9
-    assert relerr(out["quad8"][2], out["generic"][2]) < 1e-11
-    fin = np.isfinite(out["generic"][4])
-    assert np.array_equal(fin, np.isfinite(out["quad8"][4]))
-    assert relerr(out["quad8"][4][fin], out["generic"][4][fin]) < 1e-10
+        for A in (8, 4):      # 8: one CTA per trajectory with staged operands; 4: the unstaged variant
+            s = make_gpu(prob, B=B, x0=x0, A=A)
+            s.begin_solve()
+            for _ in range(3):
+                s.iterate()
+            out[mode, A] = (s.get(_lib.X_BAR), s.get(_lib.U_BAR), s.cost.copy(), s.get_int(_lib.I_LS_ITERS).copy(),
+                            s.get(_lib.CAND_COST).copy())
+    for A in (8, 4):
+        q, g = out["quad8", A], out["generic", A]
+        assert np.array_equal(q[3], g[3])
+        assert relerr(q[0], g[0]) < 1e-10
+        assert relerr(q[1], g[1]) < 1e-9
+        assert relerr(q[2], g[2]) < 1e-11
+        fin = np.isfinite(g[4])
+        assert np.array_equal(fin, np.isfinite(q[4]))
+        assert relerr(q[4][fin], g[4][fin]) < 1e-10
 
 
 def test_split_iterate_and_host_exchange_equal_iterate():
