@@ -802,32 +802,13 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
       invert_warp<m>(s.Quu, s.QuuInv);
     __syncwarp();
     BS_TICK(5);
-    if (kBsNamed || kBsBarQNamed) named_bar_sync(4, NT);
-    else {
-      if (lane == 0) mbar_arrive(&s.barQ);
-      mbar_wait(&s.barQ, parityQ);   // ... and all Q-terms complete
-    }
-    parityQ ^= 1;
-    BS_TICK(6);
-    // Qx = lx + fx' Vx ; Qu = lu + fu' Vx (ilqr.py:651-652): S' Vx came out of the W products
-    if (lane < n) s.QxM[lane] = lx0 + s.SVx[lane];
-    if (lane + 32 < n) s.QxM[lane + 32] = lx1 + s.SVx[lane + 32];
+    // Quu^-1 is what the DMMA warps are waiting for: arrive now, wait (for Qux) only where Qux is
+    // needed.  kappa, g and dV need Quu^-1 and Qu = lu + fu' Vx alone, and fu' Vx (S' Vx over the
+    // strips that hold fu columns) was complete when Quu was handed over.
+    if (!(kBsNamed || kBsBarQNamed) && lane == 0) mbar_arrive(&s.barQ);
+    // kappa = Quu^-1 Qu ; g = Qu' Quu^-1 ; dV = g Qu                        (ilqr.py:659,663)
     if (lane < m) s.Qu[lane] = lu + s.SVx[n + lane];
     __syncwarp();
-    // every DMMA warp is through its products: fx of this step is dead (the vector warp issues the
-    // TMA of the step after next into this buffer at the top of the next step)
-    if (kBsNamed) named_bar_sync(5, NT);
-    else mbar_wait(&s.barS, parityS);
-    parityS ^= 1;
-    BS_TICK(7);
-    if (!C::TMA && t > 0) {
-      for (int i = x.tid; i < n * m; i += NT)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fu[i])),
-                     "l"(x.gfu + (size_t)(t - 1) * n * m + i)
-                     : "memory");
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    // kappa = Quu^-1 Qu ; g = Qu' Quu^-1 ; dV = g Qu ; Vx = Qx - g Qux      (ilqr.py:659,663,666)
     double qu = 0.0, gr = 0.0;
     if (lane < m) {
       qu = s.Qu[lane];
@@ -852,6 +833,28 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, o);
     if (lane == 0) d.dV[(size_t)x.b * T + t] = dv;
+    BS_TICK(6);
+    if (kBsNamed || kBsBarQNamed) named_bar_sync(4, NT);
+    else mbar_wait(&s.barQ, parityQ);   // all Q-terms complete
+    parityQ ^= 1;
+    // Qx = lx + fx' Vx (ilqr.py:651): S' Vx came out of the W products
+    if (lane < n) s.QxM[lane] = lx0 + s.SVx[lane];
+    if (lane + 32 < n) s.QxM[lane + 32] = lx1 + s.SVx[lane + 32];
+    __syncwarp();
+    // every DMMA warp is through its products: fx of this step is dead (the vector warp issues the
+    // TMA of the step after next into this buffer at the top of the next step)
+    if (kBsNamed) named_bar_sync(5, NT);
+    else mbar_wait(&s.barS, parityS);
+    parityS ^= 1;
+    BS_TICK(7);
+    if (!C::TMA && t > 0) {
+      for (int i = x.tid; i < n * m; i += NT)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fu[i])),
+                     "l"(x.gfu + (size_t)(t - 1) * n * m + i)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // Vx = Qx - g Qux                                                        (ilqr.py:666)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k = lane + 32 * h;

@@ -15,6 +15,7 @@
 #include "backward_sym.cuh"
 #include "quadruped_fused.cuh"
 #include "quadruped_rollout.cuh"
+#include "arm_rollout.cuh"
 
 using namespace ddp;
 
@@ -46,6 +47,7 @@ struct ddp_solver {
   bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
   bool quad_rollout8;    // 8-lane quadruped rollout (DDP_QUAD_ROLLOUT=generic selects rollout_kernel)
   bool quad_fused;       // fused structured quadruped linearization (DDP_QUAD_LINEARIZE=fused|ad)
+  bool arm_rollout8;     // 8-lane arm + ball rollout (DDP_ARM_ROLLOUT=generic selects rollout_kernel)
   int quad_sub;          // substeps of the quadruped model (the fused linearization needs 2)
   // array table
   double* darr[16];
@@ -216,6 +218,11 @@ int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
   }
   if (s->quad_rollout8 && s->model == MODEL_QUADRUPED_QUAT) {   // the reference's n = 37 layout
     launch_rollout_quad8<true>(s, ls_base, per_traj, n_items);
+    return 0;
+  }
+  if (s->arm_rollout8 && s->model == MODEL_ARM_BALL && s->d.diag_cost) {
+    rollout_arm8_kernel<<<cdiv(n_items, kRaCands), kRaLanes * kRaCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+    s->launches++;
     return 0;
   }
   DDP_MODEL_SWITCH(s->model, return launch_rollout<Model>(s, ls_base, per_traj, n_items));
@@ -486,6 +493,8 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
     s->d.bwd_flags = (inv && std::string(inv) == "gauss-jordan") ? 1 : 0;
     const char* rmode = getenv("DDP_QUAD_ROLLOUT");
     s->quad_rollout8 = !(rmode && std::string(rmode) == "generic");
+    const char* amode = getenv("DDP_ARM_ROLLOUT");
+    s->arm_rollout8 = !(amode && std::string(amode) == "generic");
     // default: the fused structured kernel; DDP_QUAD_LINEARIZE=ad selects the generic AD kernel
     const char* mode = getenv("DDP_QUAD_LINEARIZE");
     s->quad_fused = !(mode && std::string(mode) == "ad");

@@ -617,14 +617,137 @@ struct QuadrupedQuat {
 struct ArmBall {
   static constexpr int n = 27, m = 7, np = 20;
   static constexpr int COOP = 1;
+
+  // tool frame while walking up the chain: rotation (rows x, y, z of the world axes) and origin
+  template <class S>
+  struct Frame {
+    S Rxx, Rxy, Rxz, Ryx, Ryy, Ryz, Rzx, Rzy, Rzz, px, py, pz;
+  };
+  template <class S>
+  DDP_HD static void fk_init(const S& q0, double bz, Frame<S>& F) {
+    F.Rxx = 1.0 + 0.0 * q0; F.Rxy = 0.0 * q0; F.Rxz = F.Rxy;
+    F.Ryx = F.Rxy; F.Ryy = F.Rxx; F.Ryz = F.Rxy;
+    F.Rzx = F.Rxy; F.Rzy = F.Rxy; F.Rzz = F.Rxx;
+    F.px = F.Rxy; F.py = F.Rxy; F.pz = F.Rxy + bz;
+  }
+  // joint i: rotate about axis a_i (local z for even i, local y for odd i) by the angle with sine s
+  // and cosine c, then go di along the rotated local z.  Returns the joint axis in the world frame;
+  // the joint origin is (F.px, F.py, F.pz) BEFORE the call.
+  template <class S>
+  DDP_HD static void fk_joint(int i, const S& s, const S& c, double di, Frame<S>& F, S& ax, S& ay, S& az) {
+    if ((i & 1) == 0) {  // about local z
+      ax = F.Rxz; ay = F.Ryz; az = F.Rzz;
+      S nxx = F.Rxx * c + F.Rxy * s, nxy = F.Rxy * c - F.Rxx * s;
+      S nyx = F.Ryx * c + F.Ryy * s, nyy = F.Ryy * c - F.Ryx * s;
+      S nzx = F.Rzx * c + F.Rzy * s, nzy = F.Rzy * c - F.Rzx * s;
+      F.Rxx = nxx; F.Rxy = nxy; F.Ryx = nyx; F.Ryy = nyy; F.Rzx = nzx; F.Rzy = nzy;
+    } else {  // about local y
+      ax = F.Rxy; ay = F.Ryy; az = F.Rzy;
+      S nxx = F.Rxx * c - F.Rxz * s, nxz = F.Rxz * c + F.Rxx * s;
+      S nyx = F.Ryx * c - F.Ryz * s, nyz = F.Ryz * c + F.Ryx * s;
+      S nzx = F.Rzx * c - F.Rzz * s, nzz = F.Rzz * c + F.Rzx * s;
+      F.Rxx = nxx; F.Rxz = nxz; F.Ryx = nyx; F.Ryz = nyz; F.Rzx = nzx; F.Rzz = nzz;
+    }
+    F.px = F.px + di * F.Rxz;
+    F.py = F.py + di * F.Ryz;
+    F.pz = F.pz + di * F.Rzz;
+  }
+  // contact loads: force on the tool tip, force and world-frame torque on the ball
+  template <class S>
+  struct Loads {
+    S ftx, fty, ftz, fbx, fby, fbz, tbx, tby, tbz;
+  };
+  // (px, py, pz) tool tip, (tvx, tvy, tvz) its velocity, (bx_, by_, bz_) ball centre, w / bv ball
+  // angular / linear velocity
+  template <class S>
+  DDP_HD static void contacts(const S& px, const S& py, const S& pz, const S& tvx, const S& tvy, const S& tvz,
+                              const S& bx_, const S& by_, const S& bz_, const S* w, const S* bv, const double* p,
+                              Loads<S>& o) {
+    const double rt = p[11], rb = p[12], mb = p[13], E = p[14], mu = p[15], vs = p[16];
+    const double g = p[17], diss = p[19];
+    S fbx = 0.0 * px, fby = fbx, fbz = fbx - mb * g;  // force on ball
+    S tbx = 0.0 * px, tby = tbx, tbz = tbx;           // torque on ball (world)
+    S ftx = 0.0 * px, fty = ftx, ftz = ftx;           // force on tool tip
+    // tip sphere vs ball
+    {
+      S nx = bx_ - px, ny = by_ - py, nz = bz_ - pz;
+      S dist = sqrt_(nx * nx + ny * ny + nz * nz + 1e-12);
+      S depth = (rt + rb) - dist;
+      if (val(depth) > 0.0) {
+        nx = nx / dist; ny = ny / dist; nz = nz / dist;  // tip -> ball
+        const double Re = rt * rb / (rt + rb);
+        // relative velocity of ball surface point w.r.t. tip at the contact
+        S cxr = -(rb)*nx, cyr = -(rb)*ny, czr = -(rb)*nz;  // contact point rel. ball centre
+        S rvx = bv[0] + (w[1] * czr - w[2] * cyr) - tvx;
+        S rvy = bv[1] + (w[2] * cxr - w[0] * czr) - tvy;
+        S rvz = bv[2] + (w[0] * cyr - w[1] * cxr) - tvz;
+        S vn = rvx * nx + rvy * ny + rvz * nz;   // separation rate = -depth rate
+        S Fn = sphere_plane_force(depth, Re, E);
+        S hc = 1.0 - diss * vn;
+        if (val(hc) < 0.0) hc = S(0.0);
+        Fn = Fn * hc;
+        S tx = rvx - vn * nx, ty = rvy - vn * ny, tz = rvz - vn * nz;
+        S sl = sqrt_(tx * tx + ty * ty + tz * tz + vs * vs);
+        S cfx = Fn * nx - (mu * Fn) * tx / sl;
+        S cfy = Fn * ny - (mu * Fn) * ty / sl;
+        S cfz = Fn * nz - (mu * Fn) * tz / sl;
+        fbx = fbx + cfx; fby = fby + cfy; fbz = fbz + cfz;
+        tbx = tbx + (cyr * cfz - czr * cfy);
+        tby = tby + (czr * cfx - cxr * cfz);
+        tbz = tbz + (cxr * cfy - cyr * cfx);
+        ftx = ftx - cfx; fty = fty - cfy; ftz = ftz - cfz;
+      }
+    }
+    // ball vs table (z = 0)
+    {
+      S depth = rb - bz_;
+      if (val(depth) > 0.0) {
+        S Fn = sphere_plane_force(depth, rb, E);
+        S hc = 1.0 - diss * bv[2];
+        if (val(hc) < 0.0) hc = S(0.0);
+        Fn = Fn * hc;
+        // contact point velocity: v + w x (0,0,-rb)
+        S cvx = bv[0] - w[1] * rb;
+        S cvy = bv[1] + w[0] * rb;
+        S sl = sqrt_(cvx * cvx + cvy * cvy + vs * vs);
+        S fx_ = -(mu * Fn) * cvx / sl, fy_ = -(mu * Fn) * cvy / sl;
+        fbx = fbx + fx_; fby = fby + fy_; fbz = fbz + Fn;
+        // torque = (0,0,-rb) x (fx, fy, Fn)
+        tbx = tbx + rb * fy_;
+        tby = tby - rb * fx_;
+      }
+    }
+    o.ftx = ftx; o.fty = fty; o.ftz = ftz;
+    o.fbx = fbx; o.fby = fby; o.fbz = fbz;
+    o.tbx = tbx; o.tby = tby; o.tbz = tbz;
+  }
+  // semi-implicit Euler of the free ball: vb = [w (3) | v (3)], qb = [quaternion (4) | position (3)]
+  template <class S>
+  DDP_HD static void ball_integrate(S* qb, S* vb, const Loads<S>& L, double h, double mb, double Ib) {
+    vb[0] = vb[0] + (h / Ib) * L.tbx;
+    vb[1] = vb[1] + (h / Ib) * L.tby;
+    vb[2] = vb[2] + (h / Ib) * L.tbz;
+    vb[3] = vb[3] + (h / mb) * L.fbx;
+    vb[4] = vb[4] + (h / mb) * L.fby;
+    vb[5] = vb[5] + (h / mb) * L.fbz;
+    // quaternion rate for world-frame angular velocity: qdot = 0.5 * (0,w) (x) q
+    S qw = qb[0], qx = qb[1], qy = qb[2], qz = qb[3];
+    qb[0] = qw + (0.5 * h) * (-(vb[0] * qx) - vb[1] * qy - vb[2] * qz);
+    qb[1] = qx + (0.5 * h) * (vb[0] * qw + vb[1] * qz - vb[2] * qy);
+    qb[2] = qy + (0.5 * h) * (vb[1] * qw + vb[2] * qx - vb[0] * qz);
+    qb[3] = qz + (0.5 * h) * (vb[2] * qw + vb[0] * qy - vb[1] * qx);
+    qb[4] = qb[4] + h * vb[3];
+    qb[5] = qb[5] + h * vb[4];
+    qb[6] = qb[6] + h * vb[5];
+  }
+
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {
     const int sub = (int)p[1];
     const double h = p[0] / sub;
     const double Ij = p[2], bj = p[3];
     const double* d = p + 4;
-    const double rt = p[11], rb = p[12], mb = p[13], E = p[14], mu = p[15], vs = p[16];
-    const double g = p[17], bz = p[18], diss = p[19];
+    const double rb = p[12], mb = p[13], bz = p[18];
     const double Ib = 0.4 * mb * rb * rb;
     S q[14], v[13];
 #pragma unroll
@@ -633,43 +756,24 @@ struct ArmBall {
     for (int i = 0; i < 13; ++i) v[i] = x[14 + i];
     for (int it = 0; it < sub; ++it) {
       // ---- forward kinematics of the tool tip with its position Jacobian ----
-      // frame i: rotate about axis a_i (z for even i, y for odd i), then go d_i along
-      // the rotated local z.  Keep rotation columns and accumulate joint origins.
-      S Rxx = 1.0 + 0.0 * q[0], Rxy = 0.0 * q[0], Rxz = Rxy;
-      S Ryx = Rxy, Ryy = Rxx, Ryz = Rxy;
-      S Rzx = Rxy, Rzy = Rxy, Rzz = Rxx;
+      Frame<S> F;
+      fk_init(q[0], bz, F);
       S ox[7], oy[7], oz[7], ax[7], ay[7], az[7];
-      S px = Rxy, py = Rxy, pz = Rxy + bz;
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
         S s, c;
         sincos_(q[i], &s, &c);
-        ox[i] = px;
-        oy[i] = py;
-        oz[i] = pz;
-        if ((i & 1) == 0) {  // about local z
-          ax[i] = Rxz; ay[i] = Ryz; az[i] = Rzz;
-          S nxx = Rxx * c + Rxy * s, nxy = Rxy * c - Rxx * s;
-          S nyx = Ryx * c + Ryy * s, nyy = Ryy * c - Ryx * s;
-          S nzx = Rzx * c + Rzy * s, nzy = Rzy * c - Rzx * s;
-          Rxx = nxx; Rxy = nxy; Ryx = nyx; Ryy = nyy; Rzx = nzx; Rzy = nzy;
-        } else {  // about local y
-          ax[i] = Rxy; ay[i] = Ryy; az[i] = Rzy;
-          S nxx = Rxx * c - Rxz * s, nxz = Rxz * c + Rxx * s;
-          S nyx = Ryx * c - Ryz * s, nyz = Ryz * c + Ryx * s;
-          S nzx = Rzx * c - Rzz * s, nzz = Rzz * c + Rzx * s;
-          Rxx = nxx; Rxz = nxz; Ryx = nyx; Ryz = nyz; Rzx = nzx; Rzz = nzz;
-        }
-        px = px + d[i] * Rxz;
-        py = py + d[i] * Ryz;
-        pz = pz + d[i] * Rzz;
+        ox[i] = F.px;
+        oy[i] = F.py;
+        oz[i] = F.pz;
+        fk_joint(i, s, c, d[i], F, ax[i], ay[i], az[i]);
       }
       // tip velocity = sum_i (a_i x (p - o_i)) qd_i ; keep the Jacobian columns
       S Jx[7], Jy[7], Jz[7];
-      S tvx = 0.0 * px, tvy = tvx, tvz = tvx;
+      S tvx = 0.0 * F.px, tvy = tvx, tvz = tvx;
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        S dx = px - ox[i], dy = py - oy[i], dz = pz - oz[i];
+        S dx = F.px - ox[i], dy = F.py - oy[i], dz = F.pz - oz[i];
         Jx[i] = ay[i] * dz - az[i] * dy;
         Jy[i] = az[i] * dx - ax[i] * dz;
         Jz[i] = ax[i] * dy - ay[i] * dx;
@@ -677,85 +781,18 @@ struct ArmBall {
         tvy = tvy + Jy[i] * v[i];
         tvz = tvz + Jz[i] * v[i];
       }
-      // ---- ball state ----
-      const S* w = v + 7;   // ball angular velocity (world)
-      const S* bv = v + 10; // ball linear velocity
-      S bx_ = q[11], by_ = q[12], bz_ = q[13];
-      S fbx = 0.0 * px, fby = fbx, fbz = fbx - mb * g;  // force on ball
-      S tbx = 0.0 * px, tby = tbx, tbz = tbx;           // torque on ball (world)
-      S ftx = 0.0 * px, fty = ftx, ftz = ftx;           // force on tool tip
-      // tip sphere vs ball
-      {
-        S nx = bx_ - px, ny = by_ - py, nz = bz_ - pz;
-        S dist = sqrt_(nx * nx + ny * ny + nz * nz + 1e-12);
-        S depth = (rt + rb) - dist;
-        if (val(depth) > 0.0) {
-          nx = nx / dist; ny = ny / dist; nz = nz / dist;  // tip -> ball
-          const double Re = rt * rb / (rt + rb);
-          // relative velocity of ball surface point w.r.t. tip at the contact
-          S cxr = -(rb)*nx, cyr = -(rb)*ny, czr = -(rb)*nz;  // contact point rel. ball centre
-          S rvx = bv[0] + (w[1] * czr - w[2] * cyr) - tvx;
-          S rvy = bv[1] + (w[2] * cxr - w[0] * czr) - tvy;
-          S rvz = bv[2] + (w[0] * cyr - w[1] * cxr) - tvz;
-          S vn = rvx * nx + rvy * ny + rvz * nz;   // separation rate = -depth rate
-          S Fn = sphere_plane_force(depth, Re, E);
-          S hc = 1.0 - diss * vn;
-          if (val(hc) < 0.0) hc = S(0.0);
-          Fn = Fn * hc;
-          S tx = rvx - vn * nx, ty = rvy - vn * ny, tz = rvz - vn * nz;
-          S sl = sqrt_(tx * tx + ty * ty + tz * tz + vs * vs);
-          S cfx = Fn * nx - (mu * Fn) * tx / sl;
-          S cfy = Fn * ny - (mu * Fn) * ty / sl;
-          S cfz = Fn * nz - (mu * Fn) * tz / sl;
-          fbx = fbx + cfx; fby = fby + cfy; fbz = fbz + cfz;
-          tbx = tbx + (cyr * cfz - czr * cfy);
-          tby = tby + (czr * cfx - cxr * cfz);
-          tbz = tbz + (cxr * cfy - cyr * cfx);
-          ftx = ftx - cfx; fty = fty - cfy; ftz = ftz - cfz;
-        }
-      }
-      // ball vs table (z = 0)
-      {
-        S depth = rb - bz_;
-        if (val(depth) > 0.0) {
-          S Fn = sphere_plane_force(depth, rb, E);
-          S hc = 1.0 - diss * bv[2];
-          if (val(hc) < 0.0) hc = S(0.0);
-          Fn = Fn * hc;
-          // contact point velocity: v + w x (0,0,-rb)
-          S cvx = bv[0] - w[1] * rb;
-          S cvy = bv[1] + w[0] * rb;
-          S sl = sqrt_(cvx * cvx + cvy * cvy + vs * vs);
-          S fx_ = -(mu * Fn) * cvx / sl, fy_ = -(mu * Fn) * cvy / sl;
-          fbx = fbx + fx_; fby = fby + fy_; fbz = fbz + Fn;
-          // torque = (0,0,-rb) x (fx, fy, Fn)
-          tbx = tbx + rb * fy_;
-          tby = tby - rb * fx_;
-        }
-      }
+      // ---- contacts: tip sphere vs ball, ball vs table ----
+      Loads<S> L;
+      contacts(F.px, F.py, F.pz, tvx, tvy, tvz, q[11], q[12], q[13], v + 7, v + 10, p, L);
       // ---- accelerations, semi-implicit Euler ----
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        S tau = u[i] + Jx[i] * ftx + Jy[i] * fty + Jz[i] * ftz - bj * v[i];
+        S tau = u[i] + Jx[i] * L.ftx + Jy[i] * L.fty + Jz[i] * L.ftz - bj * v[i];
         v[i] = v[i] + (h / Ij) * tau;
       }
-      v[7] = v[7] + (h / Ib) * tbx;
-      v[8] = v[8] + (h / Ib) * tby;
-      v[9] = v[9] + (h / Ib) * tbz;
-      v[10] = v[10] + (h / mb) * fbx;
-      v[11] = v[11] + (h / mb) * fby;
-      v[12] = v[12] + (h / mb) * fbz;
 #pragma unroll
       for (int i = 0; i < 7; ++i) q[i] = q[i] + h * v[i];
-      // quaternion rate for world-frame angular velocity: qdot = 0.5 * (0,w) (x) q
-      S qw = q[7], qx = q[8], qy = q[9], qz = q[10];
-      q[7] = qw + (0.5 * h) * (-(v[7] * qx) - v[8] * qy - v[9] * qz);
-      q[8] = qx + (0.5 * h) * (v[7] * qw + v[8] * qz - v[9] * qy);
-      q[9] = qy + (0.5 * h) * (v[8] * qw + v[9] * qx - v[7] * qz);
-      q[10] = qz + (0.5 * h) * (v[9] * qw + v[7] * qy - v[8] * qx);
-      q[11] = q[11] + h * v[10];
-      q[12] = q[12] + h * v[11];
-      q[13] = q[13] + h * v[12];
+      ball_integrate(q + 7, v + 7, L, h, mb, Ib);
     }
 #pragma unroll
     for (int i = 0; i < 14; ++i) xn[i] = q[i];

@@ -146,7 +146,9 @@ class BatchedILQR:
             # as that (8 for the quadruped kernels: their CTA is 8 candidates of one trajectory, and
             # 8 resolve > 90 % of the trajectories), within 2 GiB of candidate buffer.
             per_rollout = 8 * (self.N * self.n + self.T * self.m)
-            quad = self.system.model_id in (4, 6)       # quadruped, quadruped_quat: the 8-lane rollout
+            # quadruped, quadruped_quat, arm_ball: the 8-lane rollouts; 8 candidates per trajectory
+            # keep a 512..1024-trajectory batch within one resident wave of their CTAs
+            quad = self.system.model_id in (4, 5, 6)
             lanes = 1 if (self.n + self.m) <= 8 else (8 if quad else 4)
             wave = 148 * 2048 // max(1, self.B * lanes)
             cap = 8 if quad else n_eps

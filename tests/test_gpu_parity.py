@@ -397,6 +397,35 @@ def test_quadruped_rollout8_matches_generic_rollout(monkeypatch, name):
         assert relerr(q[4][fin], g[4][fin]) < 1e-10
 
 
+def test_arm_rollout8_matches_generic_rollout(monkeypatch):
+    """The 8-lane arm + ball rollout (csrc/arm_rollout.cuh, config C5) against the generic rollout
+    kernel: same candidates, same accepted step, states equal up to the association of the tool-tip
+    velocity / feedback / cost sums.  A non-diagonal cost takes the generic kernel either way."""
+    prob = problems.arm_ball(120)
+    B = 5
+    x0 = prob.batch_x0(B, seed=3)
+    out = {}
+    for mode in ("arm8", "generic"):
+        monkeypatch.delenv("DDP_ARM_ROLLOUT", raising=False)
+        if mode == "generic":
+            monkeypatch.setenv("DDP_ARM_ROLLOUT", "generic")
+        s = make_gpu(prob, B=B, x0=x0, A=6)
+        s.begin_solve()
+        for _ in range(3):
+            s.iterate()
+        out[mode] = (s.get(_lib.X_BAR), s.get(_lib.U_BAR), s.cost.copy(), s.get_int(_lib.I_LS_ITERS).copy(),
+                     s.get(_lib.CAND_COST).copy(), s.get(_lib.CAND_X).copy())
+    q, g = out["arm8"], out["generic"]
+    assert np.array_equal(q[3], g[3])
+    assert relerr(q[0], g[0]) < 1e-10
+    assert relerr(q[1], g[1]) < 1e-9
+    assert relerr(q[2], g[2]) < 1e-11
+    fin = np.isfinite(g[4])
+    assert np.array_equal(fin, np.isfinite(q[4]))
+    assert relerr(q[4][fin], g[4][fin]) < 1e-10
+    assert relerr(q[5], g[5]) < 1e-9
+
+
 def test_split_iterate_and_host_exchange_equal_iterate():
     """ddp_iterate_linesearch / _finish_async / _wait with the overlapped host exchange
     (HostExchange: staged upload, control read-back under the backward pass) give bit-identical
