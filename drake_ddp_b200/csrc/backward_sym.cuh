@@ -43,6 +43,8 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 __device__ __forceinline__ double ldz(const double* P, int ld, int r, int c, int R, int C) {
   return (r < R && c < C) ? P[r * ld + c] : 0.0;
 }
+// position of column j (or of the even-aligned column pair starting at j) of row k in a W / K strip
+__device__ __forceinline__ int bs_wcol(int k, int j) { return j ^ ((k & 2) << 1); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -143,8 +145,22 @@ struct BsCfg {
   static constexpr int TQ = n / 8;                     // first stacked strip that holds an fu column
   static constexpr int NMW = 3, NW = NMW + 1, NT = NW * 32;  // 3 DMMA warps + the vector warp
   static_assert(TS <= 8 && TN <= 8, "strip lists hold 8 entries");
-  // bulk TMA needs 16-byte sizes and 16-byte aligned tile starts in global memory
-  static constexpr bool TMA = ((n * n) % 2 == 0) && ((n * m) % 2 == 0);
+  // Bulk TMA needs 16-byte sizes and 16-byte aligned addresses on both sides.  A tile with an odd
+  // number of doubles (n = 37: fx; n = 27, m = 7: fx and fu) starts 16-byte aligned only at every
+  // other step: its copy is rounded out to the enclosing 16-byte window (one double more, before or
+  // after the tile; the arrays are 256-byte aligned and carry 16 bytes of slack) and the tile then
+  // starts at element 0 or 1 of the buffer.  -DDDP_BWD_NO_TMA: 8-byte cp.async copies by all threads
+  // instead (the round-1 path for odd sizes; 17 % slower at n = 36).
+#ifdef DDP_BWD_NO_TMA
+  static constexpr bool TMA = false;
+#else
+  static constexpr bool TMA = true;
+#endif
+  static constexpr bool ODD_FX = (n * n) % 2 != 0, ODD_FU = (n * m) % 2 != 0;
+  static constexpr uint32_t FX_BYTES = (n * n + (ODD_FX ? 1 : 0)) * 8, FU_BYTES = (n * m + (ODD_FU ? 1 : 0)) * 8;
+  // tile `idx` (= b T + t) of an array of tiles of `elems` doubles: first double of the 16-byte
+  // window that holds its start, and where the tile starts inside the window (0 or 1)
+  static __device__ __forceinline__ int tile_pre(size_t idx, int elems) { return (int)((idx * (size_t)elems) & 1); }
   static constexpr bool EVEN = (n % 2 == 0) && (m % 2 == 0);  // C-fragment pairs never straddle n or rows
   static constexpr int even(int v) { return (v + 1) & ~1; }
   // stacked strips dealt to the DMMA warps: W_c, the tiles M(r <= c, c) and, for c < TN, the
@@ -170,6 +186,10 @@ struct BsSmem {
   alignas(16) double Vxx[C::even(n * C::LDV)];
   // W_c = Vxx S_c, one private [n][8] slice per stacked strip; once the Q-terms exist the same
   // memory holds the column strips of K, [m][8] each
+  // Column j of row k sits at position j ^ (4 * bit1(k)) of the row (bs_wcol): the B-operand fetch
+  // of an m8n8k4 DMMA reads rows k = 4 kk + tg, columns g, and a half-warp (g = 0..3, all tg) of
+  // 8-byte accesses must cover 32 distinct banks; in the plain [k][8] layout rows tg and tg + 2 of
+  // a half-warp share their banks (2-way conflict: 35 M of 481 M wavefronts per launch in r2a)
   alignas(16) double Wf[C::TS * n * 8];
   alignas(16) double Qux[C::even(m * n)];
   alignas(16) double Quu[C::even(m * m)];
@@ -327,6 +347,7 @@ struct BsCtx {
   BsSmem<n, m>* s;
   Dev d;
   int b, lane, g, tg, tid;
+  size_t tile0;   // index of the trajectory's first (b, t) tile: b T
   const double *Q, *R, *gfx, *gfu, *gxb, *gub, *xnom;
   bool diag;
 };
@@ -408,8 +429,8 @@ __device__ __forceinline__ void bs_w_strips(BsSmem<n, m>& s, const double* Fx, c
   for (int i = 0; i < TN; ++i) {
     const int r = 8 * i + g;
     if (r < n) {
-      *reinterpret_cast<double2*>(w0 + r * 8 + 2 * tg) = make_double2(acc[i][0][0], acc[i][0][1]);
-      if (two) *reinterpret_cast<double2*>(w1 + r * 8 + 2 * tg) = make_double2(acc[i][1][0], acc[i][1][1]);
+      *reinterpret_cast<double2*>(w0 + r * 8 + bs_wcol(r, 2 * tg)) = make_double2(acc[i][0][0], acc[i][0][1]);
+      if (two) *reinterpret_cast<double2*>(w1 + r * 8 + bs_wcol(r, 2 * tg)) = make_double2(acc[i][1][0], acc[i][1][1]);
     } else if (r == n) {
       *reinterpret_cast<double2*>(s.SVx + 8 * c0 + 2 * tg) = make_double2(acc[i][0][0], acc[i][0][1]);
       if (two) *reinterpret_cast<double2*>(s.SVx + 8 * c1 + 2 * tg) = make_double2(acc[i][1][0], acc[i][1][1]);
@@ -453,8 +474,8 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
                      : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    const double* Fx = s.Fx[buf];
-    const double* Fu = s.Fu;
+    const double* Fx = s.Fx[buf] + ((C::TMA && C::ODD_FX) ? C::tile_pre(x.tile0 + t, n * n) : 0);
+    const double* Fu = s.Fu + ((C::TMA && C::ODD_FU) ? C::tile_pre(x.tile0 + t, n * m) : 0);
 
     // ---- phase 1, first part: W_c = Vxx S_c for the strips that hold fu columns (c >= TQ): Quu
     // = luu + fu' Vxx fu starts the serial path of the step (Quu -> its inverse -> K -> Vxx) and
@@ -471,7 +492,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
     for (int p0 = 0; p0 < NSTR; ++p0) {
       const int c = SD.list[W][p0];
       if (c < TQ) continue;
-      const double* pw = s.Wf + c * (n * 8) + tg * 8 + g;
+      const double* pw = s.Wf + c * (n * 8) + tg * 8 + bs_wcol(tg, g);   // rows 4 kk + tg: bit 1 is tg's
       const double* pa[TS - TQ];
       int sa[TS - TQ];
 #pragma unroll
@@ -516,7 +537,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
 #pragma unroll
       for (int p0 = 0; p0 < C::MAXS; ++p0) {
         const int c = SD.list[W][p0 < NSTR ? p0 : 0];
-        pw[p0] = s.Wf + c * (n * 8) + tg * 8 + g;
+        pw[p0] = s.Wf + c * (n * 8) + tg * 8 + bs_wcol(tg, g);
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) acc[p0][r][0] = acc[p0][r][1] = 0.0;
       }
@@ -637,7 +658,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
         for (int i = 0; i < TM; ++i) {
           const int r = 8 * i + g, col = 8 * c + 2 * tg;
           if (r < m) {
-            *reinterpret_cast<double2*>(kt + r * 8 + 2 * tg) = make_double2(kacc[p0][i][0], kacc[p0][i][1]);
+            *reinterpret_cast<double2*>(kt + r * 8 + bs_wcol(r, 2 * tg)) = make_double2(kacc[p0][i][0], kacc[p0][i][1]);
             if (EVEN) {
               if (col < n) *reinterpret_cast<double2*>(gK + r * n + col) = make_double2(kacc[p0][i][0], kacc[p0][i][1]);
             } else {
@@ -655,7 +676,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
 #pragma unroll
       for (int p0 = 0; p0 < C::MAXK; ++p0) {
         const int c = KD.list[W][p0 < NKST ? p0 : 0];
-        pk[p0] = s.Wf + c * (n * 8) + tg * 8 + g;
+        pk[p0] = s.Wf + c * (n * 8) + tg * 8 + bs_wcol(tg, g);
 #pragma unroll
         for (int r = 0; r < TN; ++r) acc[p0][r][0] = acc[p0][r][1] = 0.0;
       }
@@ -739,8 +760,9 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
     BS_TICK(0);
     if (C::TMA) {
       if (lane == 0 && t > 0) {   // next step's fx into the other half of the double buffer
-        mbar_expect_tx(&s.bar[buf ^ 1], n * n * 8);
-        tma_load_1d(s.Fx[buf ^ 1], x.gfx + (size_t)(t - 1) * n * n, n * n * 8, &s.bar[buf ^ 1]);
+        mbar_expect_tx(&s.bar[buf ^ 1], C::FX_BYTES);
+        tma_load_1d(s.Fx[buf ^ 1], x.gfx + (size_t)(t - 1) * n * n - C::tile_pre(x.tile0 + t - 1, n * n), C::FX_BYTES,
+                    &s.bar[buf ^ 1]);
       }
       mbar_wait(&s.bar[buf], parity[buf]);
       parity[buf] ^= 1;
@@ -795,8 +817,8 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
     // fu is only read by the strips / row tiles that hold fu columns, and those are done once Quu
     // exists: refill the single Fu buffer now, a whole inversion ahead of its next use
     if (C::TMA && lane == 0 && t > 0) {
-      mbar_expect_tx(&s.barFu, n * m * 8);
-      tma_load_1d(s.Fu, x.gfu + (size_t)(t - 1) * n * m, n * m * 8, &s.barFu);
+      mbar_expect_tx(&s.barFu, C::FU_BYTES);
+      tma_load_1d(s.Fu, x.gfu + (size_t)(t - 1) * n * m - C::tile_pre(x.tile0 + t - 1, n * m), C::FU_BYTES, &s.barFu);
     }
     if (t == T - 1 || (d.bwd_flags & 1) || !invert_newton_warp<m>(s.Quu, s.QuuInv, s.NsR))
       invert_warp<m>(s.Quu, s.QuuInv);
@@ -899,6 +921,7 @@ backward_sym_kernel(Dev d) {
   x.R = d.R;
   x.diag = d.diag_cost != 0;
   x.xnom = d.x_nom + (size_t)b * n;
+  x.tile0 = (size_t)b * T;
   x.gfx = d.fx + (size_t)b * T * n * n;
   x.gfu = d.fu + (size_t)b * T * n * m;
   x.gxb = d.x_bar + (size_t)b * N * n;
@@ -942,10 +965,10 @@ backward_sym_kernel(Dev d) {
   const int role = (warp - slot - 1) & 3;   // 0..2: DMMA warps; 3 (warp == slot): the vector warp
   if (C::TMA) {
     if (role == NMW && lane == 0) {
-      mbar_expect_tx(&s.bar[0], n * n * 8);
-      tma_load_1d(s.Fx[0], x.gfx + (size_t)(T - 1) * n * n, n * n * 8, &s.bar[0]);
-      mbar_expect_tx(&s.barFu, n * m * 8);
-      tma_load_1d(s.Fu, x.gfu + (size_t)(T - 1) * n * m, n * m * 8, &s.barFu);
+      mbar_expect_tx(&s.bar[0], C::FX_BYTES);
+      tma_load_1d(s.Fx[0], x.gfx + (size_t)(T - 1) * n * n - C::tile_pre(x.tile0 + T - 1, n * n), C::FX_BYTES, &s.bar[0]);
+      mbar_expect_tx(&s.barFu, C::FU_BYTES);
+      tma_load_1d(s.Fu, x.gfu + (size_t)(T - 1) * n * m - C::tile_pre(x.tile0 + T - 1, n * m), C::FU_BYTES, &s.barFu);
     }
   } else {
     for (int i = tid; i < n * n; i += NT)

@@ -78,7 +78,9 @@ struct Carver {
   T* take(size_t count) {
     off = (off + 255) & ~(size_t)255;
     T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += count * sizeof(T);
+    // 16 bytes of slack: the bulk copies of odd-sized fx / fu tiles are rounded out to 16-byte
+    // boundaries and may read 8 bytes past the last tile of an array (backward_sym.cuh)
+    off += count * sizeof(T) + 16;
     return p;
   }
 };

@@ -300,6 +300,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       ROLL_TICK(4);
       Qd::BasePose<double> B;
       double vb[6];   // [world linear velocity | body angular velocity]: what the legs want
+      double icp = 1.0, tp = 0.0;
       if (!QUAT) {
         B.sr = __shfl_sync(mask, s2, gbase + 1);
         B.cr = __shfl_sync(mask, c2, gbase + 1);
@@ -309,6 +310,8 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
         Qd::base_pose_trig(sy, cy, B);
 #pragma unroll
         for (int k = 0; k < 6; ++k) vb[k] = s.x[18 + k];
+        icp = 1.0 / B.cp;   // a division is ~25 dependent instructions: started here it runs under the leg chain
+        tp = B.sp * icp;
       } else {
         // rotation matrix of the normalised quaternion (QuadrupedQuat::step), every lane
         const double q0 = s.x[0], q1 = s.x[1], q2 = s.x[2], q3 = s.x[3];
@@ -349,15 +352,12 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       const double n3 = f[3] - (Iz - Iy) * vb[4] * vb[5];
       const double n4 = f[4] - (Ix - Iz) * vb[5] * vb[3];
       const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
-      double icp = 1.0, tp = 0.0;
       if (!QUAT) {   // Quadruped::base_acc: [linear | body angular]
         const double num = (lane == 0) ? f[0] : (lane == 1) ? f[1] : (lane == 2) ? f[2] : (lane == 3) ? n3 : (lane == 4) ? n4 : n5;
         const double rcp = (lane < 3) ? p[20] : (lane == 3) ? p[21] : (lane == 4) ? p[22] : p[23];
         double a = num * rcp;
         if (lane == 2) a -= grav;
         if (lane < 6) s.acc[lane] = a;
-        icp = 1.0 / B.cp;
-        tp = B.sp * icp;
       } else {       // QuadrupedQuat::step: [world angular = R (body angular) | linear]
         const double ab0 = n3 * p[21], ab1 = n4 * p[22], ab2 = n5 * p[23];
         const double r0 = (lane == 0) ? B.R00 : (lane == 1) ? B.R10 : B.R20;
