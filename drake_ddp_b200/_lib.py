@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DDP_B200_LIB") or os.path.join(_HERE, "libddp_b200.so")
 _CSRC = os.path.join(_HERE, "csrc")
 _SOURCES = [os.path.join(_CSRC, "ddp_api.cu")]
-_DEPS = _SOURCES + [os.path.join(_CSRC, f) for f in ("kernels.cuh", "backward_sym.cuh", "quadruped_fused.cuh", "quadruped_rollout.cuh", "arm_rollout.cuh", "models.h", "dual.h")] + [
+_DEPS = _SOURCES + [os.path.join(_CSRC, f) for f in ("kernels.cuh", "backward_sym.cuh", "quadruped_fused.cuh", "quadruped_quat_fused.cuh", "quadruped_rollout.cuh", "arm_rollout.cuh", "models.h", "dual.h")] + [
     os.path.join(_HERE, "..", "include", "ddp_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -16,6 +16,7 @@
 #include "quadruped_fused.cuh"
 #include "quadruped_rollout.cuh"
 #include "arm_rollout.cuh"
+#include "quadruped_quat_fused.cuh"
 
 using namespace ddp;
 
@@ -249,8 +250,28 @@ int launch_quad_fused(ddp_solver* s, const int* list, const int* count) {
   s->launches++;
   return 0;
 }
+int launch_quad_quat_fused(ddp_solver* s, const int* list, const int* count) {
+  const size_t smem = sizeof(QqWarpSmem) * kQfWarps;
+  if (!s->fused_ctas) {
+    cudaError_t e = cudaFuncSetAttribute(quad_quat_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_err = std::string("cudaFuncSetAttribute(quad_quat_fused): ") + cudaGetErrorString(e);
+      return DDP_ERR_CUDA;
+    }
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quad_quat_fused_kernel, kQfWarps * 32, smem);
+    s->fused_ctas = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int n_items = s->d.B * s->d.T;
+  const int grid = std::min(s->fused_ctas, cdiv(n_items, kQfWarps));
+  quad_quat_fused_kernel<<<grid, kQfWarps * 32, smem, s->stream>>>(s->d, list, count, n_items);
+  s->launches++;
+  return 0;
+}
 int do_linearize(ddp_solver* s, const int* list, const int* count) {
   if (s->model == MODEL_QUADRUPED && s->quad_sub == 2 && s->quad_fused) return launch_quad_fused(s, list, count);
+  if (s->model == MODEL_QUADRUPED_QUAT && s->quad_sub == 2 && s->quad_fused) return launch_quad_quat_fused(s, list, count);
   DDP_MODEL_SWITCH(s->model, return launch_linearize<Model>(s, list, count));
   return 0;
 }
@@ -486,7 +507,7 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   double* params;
   carve(d, &params, np, c);
   s->quad_sub = 0;
-  if (model_id == MODEL_QUADRUPED) {
+  if (model_id == MODEL_QUADRUPED || model_id == MODEL_QUADRUPED_QUAT) {
     const int sub = (int)params_host[1];
     if (sub == 1 || sub == 2) s->quad_sub = sub;
   }

@@ -342,6 +342,38 @@ def test_quadruped_fused_linearization_matches_ad_kernel(monkeypatch):
             assert np.abs(out["fused"][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max())
 
 
+def test_quadruped_quat_fused_linearization_matches_ad_kernel(monkeypatch):
+    """The fused linearization of the reference's n = 37 quaternion layout (leg derivatives along 16
+    intermediate directions, mapped to state coordinates through the quaternion / body-frame
+    relations, DMMA chain; csrc/quadruped_quat_fused.cuh, the default) against the generic
+    forward-mode-AD kernel (DDP_QUAD_LINEARIZE=ad) and the host AD, on points in contact and in
+    flight with tilted, NON-unit quaternions and nonzero angular velocity."""
+    prob = problems.quadruped_quat(60)
+    B = 16
+    rng = np.random.default_rng(7)
+    x = prob.x0[None, None] + 0.05 * rng.standard_normal((B, prob.N, 37))
+    x[:, :, 0:4] += 0.1 * rng.standard_normal((B, prob.N, 4))      # tilted, |q| != 1
+    x[:, :, 19:22] += 0.5 * rng.standard_normal((B, prob.N, 3))     # spinning
+    x[B // 2:, :, 6] += 0.05                                          # second half airborne
+    u = prob.u_guess.T[None] + 2.0 * rng.standard_normal((B, prob.N - 1, 12))
+    out = {}
+    for mode in ("ad", "fused"):
+        monkeypatch.setenv("DDP_QUAD_LINEARIZE", mode)
+        s = make_gpu(prob, B=B)
+        s.put(_lib.X_BAR, x)
+        s.put(_lib.U_BAR, u)
+        s.run_phase(_lib.PHASE_DERIVATIVES)
+        out[mode] = (s.get(_lib.FX), s.get(_lib.FU))
+    o = make_oracle(prob)
+    assert relerr(out["fused"][0], out["ad"][0]) < 1e-11
+    assert relerr(out["fused"][1], out["ad"][1]) < 1e-11
+    for b in (0, B - 1):
+        for t in (0, 17, 58):
+            fxo, fuo = o.dyn.jac(x[b, t], u[b, t])
+            assert np.abs(out["fused"][0][b, t] - fxo).max() < 1e-10 * max(1.0, np.abs(fxo).max())
+            assert np.abs(out["fused"][1][b, t] - fuo).max() < 1e-10 * max(1.0, np.abs(fuo).max())
+
+
 def test_backward_newton_schulz_inverse_matches_gauss_jordan(monkeypatch):
     """backward_mma_kernel inverts Quu by Newton-Schulz on the tensor pipe, seeded with the inverse
     of the previous step, and falls back to Gauss-Jordan with partial pivoting when the seed does
