@@ -357,6 +357,8 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     sampler = ClockSampler(local)              # started before any warm-up
     prob = workload(args)

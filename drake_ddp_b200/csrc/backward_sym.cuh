@@ -156,6 +156,11 @@ struct BsCfg {
 #else
   static constexpr bool TMA = true;
 #endif
+  // fx buffers: two (the next tile travels while the step computes) up to n = 36; ONE above, where
+  // two would cost the fourth CTA per SM (n = 37: 61.6 KB against 50.6 KB): the next tile is then
+  // requested as soon as every DMMA warp is through its products (barS) and lands under the gains /
+  // Vxx update and the other CTAs of the SM
+  static constexpr int NFX = (TMA && n > 36) ? 1 : 2;
   static constexpr bool ODD_FX = (n * n) % 2 != 0, ODD_FU = (n * m) % 2 != 0;
   static constexpr uint32_t FX_BYTES = (n * n + (ODD_FX ? 1 : 0)) * 8, FU_BYTES = (n * m + (ODD_FU ? 1 : 0)) * 8;
   // tile `idx` (= b T + t) of an array of tiles of `elems` doubles: first double of the 16-byte
@@ -173,7 +178,10 @@ struct BsCfg {
 #ifndef DDP_BWD_MINB
 #define DDP_BWD_MINB 4
 #endif
-  static constexpr int MINB = (n <= 36) ? DDP_BWD_MINB : 3;  // CTAs per SM the register budget is sized for
+#ifndef DDP_BWD_MINB_BIG
+#define DDP_BWD_MINB_BIG 4
+#endif
+  static constexpr int MINB = (n <= 36) ? DDP_BWD_MINB : DDP_BWD_MINB_BIG;  // CTAs per SM the register budget is sized for
   static_assert(n <= 64 && m <= 32, "vector warp keeps lx in two registers per lane and lu in one");
   static_assert(n % 8 != 0, "Vx rides along as row n of the last (partly empty) row tile of Vxx");
 };
@@ -181,7 +189,7 @@ struct BsCfg {
 template <int n, int m>
 struct BsSmem {
   typedef BsCfg<n, m> C;
-  alignas(16) double Fx[2][C::even(n * n)];   // double-buffered bulk-TMA destination
+  alignas(16) double Fx[C::NFX][C::even(n * n)];   // bulk-TMA destination (double-buffered up to n = 36)
   alignas(16) double Fu[C::even(n * m)];      // single buffer: refilled once the Q-terms exist
   alignas(16) double Vxx[C::even(n * C::LDV)];
   // W_c = Vxx S_c, one private [n][8] slice per stacked strip; once the Q-terms exist the same
@@ -453,7 +461,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
   (void)parityS;
   int buf = 0;
   BS_PROF_DECL
-  for (int t = T - 1; t >= 0; --t, buf ^= 1) {
+  for (int t = T - 1; t >= 0; --t, buf = (buf ^ 1) & (C::NFX - 1)) {
     BS_TICK(0);
     // ---- inputs of this step: fx (TMA), fu, and the Vxx / Vx the previous step left -------------
     if (C::TMA) {
@@ -469,7 +477,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
     BS_TICK(2);
     if (!C::TMA && t > 0) {   // the next step's fx starts travelling into the other half
       for (int i = x.tid; i < n * n; i += NT)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fx[buf ^ 1][i])),
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fx[(buf ^ 1) & (C::NFX - 1)][i])),
                      "l"(x.gfx + (size_t)(t - 1) * n * n + i)
                      : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -756,13 +764,13 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
   uint32_t parity[2] = {0, 0}, parityFu = 0, parityQ = 0, parityS = 0;
   int buf = 0;
   BS_PROF_DECL
-  for (int t = T - 1; t >= 0; --t, buf ^= 1) {
+  for (int t = T - 1; t >= 0; --t, buf = (buf ^ 1) & (C::NFX - 1)) {
     BS_TICK(0);
     if (C::TMA) {
-      if (lane == 0 && t > 0) {   // next step's fx into the other half of the double buffer
+      if (C::NFX == 2 && lane == 0 && t > 0) {   // next step's fx into the other half of the double buffer
         mbar_expect_tx(&s.bar[buf ^ 1], C::FX_BYTES);
-        tma_load_1d(s.Fx[buf ^ 1], x.gfx + (size_t)(t - 1) * n * n - C::tile_pre(x.tile0 + t - 1, n * n), C::FX_BYTES,
-                    &s.bar[buf ^ 1]);
+        tma_load_1d(s.Fx[(buf ^ 1) & (C::NFX - 1)], x.gfx + (size_t)(t - 1) * n * n - C::tile_pre(x.tile0 + t - 1, n * n),
+                    C::FX_BYTES, &s.bar[buf ^ 1]);
       }
       mbar_wait(&s.bar[buf], parity[buf]);
       parity[buf] ^= 1;
@@ -776,7 +784,7 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
     BS_TICK(2);
     if (!C::TMA && t > 0) {
       for (int i = x.tid; i < n * n; i += NT)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fx[buf ^ 1][i])),
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fx[(buf ^ 1) & (C::NFX - 1)][i])),
                      "l"(x.gfx + (size_t)(t - 1) * n * n + i)
                      : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -869,6 +877,10 @@ __device__ __forceinline__ void bs_vector_warp(const BsCtx<n, m>& x) {
     else mbar_wait(&s.barS, parityS);
     parityS ^= 1;
     BS_TICK(7);
+    if (C::TMA && C::NFX == 1 && lane == 0 && t > 0) {   // single fx buffer: free now, refill it
+      mbar_expect_tx(&s.bar[0], C::FX_BYTES);
+      tma_load_1d(s.Fx[0], x.gfx + (size_t)(t - 1) * n * n - C::tile_pre(x.tile0 + t - 1, n * n), C::FX_BYTES, &s.bar[0]);
+    }
     if (!C::TMA && t > 0) {
       for (int i = x.tid; i < n * m; i += NT)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.Fu[i])),
