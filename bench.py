@@ -355,10 +355,18 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    # stdout carries ONE JSON line: whatever libraries print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) is sent to stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         # stdout carries ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the path's one collective is an 8 KB all-gather: one channel is plenty, and every NCCL CTA
+        # takes residency from the rollout (1024 CTAs on 1036 slots) while it spins for its peer
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     sampler = ClockSampler(local)              # started before any warm-up
     prob = workload(args)
@@ -548,7 +556,8 @@ def run_b200(args):
                 "sample": f"{cpu_per_proc * procs} trajectories ({cpu_per_proc} per process, {procs} processes, 1 thread each) x {cpu_steps} "
                           f"iLQR iterations of the same C4 problem after 1 warm-up iteration, same re-arm rule "
                           f"({cunits} trajectory-iterations in {cdt:.1f} s wall)"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

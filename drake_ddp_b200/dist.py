@@ -60,34 +60,39 @@ class CostGather:
         self.equal = min(self.sizes) == self.pad
         self.cost = solver.device_tensor(_lib.COST)
         dev = self.cost.device
-        self.snap = torch.zeros(self.pad, dtype=torch.float64, device=dev)
-        self.out = torch.empty(self.world * self.pad, dtype=torch.float64, device=dev)
+        # two snapshot / output pairs used in turn: the solver's stream only ever waits for the gather
+        # issued TWO iterations ago, so a rank that runs ahead by a step is not held back by its peer
+        self.snap = [torch.zeros(self.pad, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.out = [torch.empty(self.world * self.pad, dtype=torch.float64, device=dev) for _ in range(2)]
         self.side = torch.cuda.Stream(device=dev)
-        self.ev_snap = torch.cuda.Event()
-        self.ev_done = torch.cuda.Event()
-        self.pending = False
+        self.ev_snap = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.issued = 0
 
     def issue(self):
         torch = self.torch
         st = self.solver._stream
+        k = self.issued & 1
         with torch.cuda.stream(st):
-            if self.pending:
-                st.wait_event(self.ev_done)          # the previous gather has read the snapshot
-            self.snap[: self.cost.numel()].copy_(self.cost, non_blocking=True)
-            self.ev_snap.record(st)
+            if self.issued >= 2:
+                st.wait_event(self.ev_done[k])       # the gather that last used this pair has read its snapshot
+            self.snap[k][: self.cost.numel()].copy_(self.cost, non_blocking=True)
+            self.ev_snap[k].record(st)
         with torch.cuda.stream(self.side):
-            self.side.wait_event(self.ev_snap)
-            self.dist.all_gather_into_tensor(self.out, self.snap, group=self.group)
-            self.ev_done.record(self.side)
-        self.pending = True
+            self.side.wait_event(self.ev_snap[k])
+            self.dist.all_gather_into_tensor(self.out[k], self.snap[k], group=self.group)
+            self.ev_done[k].record(self.side)
+        self.issued += 1
 
     def result(self):
         """Global cost vector in batch order (waits for the gather issued last)."""
-        if self.pending:
-            self.ev_done.synchronize()
+        assert self.issued > 0, "issue() first"
+        k = (self.issued - 1) & 1
+        self.ev_done[k].synchronize()
+        out = self.out[k]
         if self.equal:
-            return self.out
-        return self.torch.cat([self.out[r * self.pad: r * self.pad + self.sizes[r]] for r in range(self.world)])
+            return out
+        return self.torch.cat([out[r * self.pad: r * self.pad + self.sizes[r]] for r in range(self.world)])
 
 
 class ShardedILQR:

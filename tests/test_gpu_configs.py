@@ -284,3 +284,16 @@ def test_device_mpc_rearm_matches_reference_mpc_loop(name):
             assert relerr(s.get(_lib.U_BAR)[b], o.u_bar) < 1e-5
             np.testing.assert_allclose(s.get(_lib.X0)[b], o.x0, rtol=1e-6, atol=1e-9)
             np.testing.assert_allclose(s.get(_lib.X_NOM)[b], o.x_nom, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cost_gather_side_stream():
+    """dist.CostGather (side-stream all-gather of the per-trajectory costs, ping-pong snapshots) on a
+    one-rank NCCL group, in a subprocess so that the process group does not leak into the suite."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "cost_gather_single.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "cost gather ok" in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
