@@ -94,6 +94,27 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   // Points are taken grid-stride; the indices of the next point are fetched at the top of the
   // current one and its state and controls after the first substep, so that the global-memory
   // latency hides behind the arithmetic (8 warps per SM cannot hide it otherwise).
+  // per-lane constants of the gyroscopic entries (lanes 0..5): row 3 + lane / 2, column and angular
+  // velocity component by the cross-product pattern, coefficient -h (I_a - I_b) / I_row
+  int gy_off = 0, gy_w = 0;
+  double gy_coef = 0.0;
+  {
+    const int rr = 3 + (lane % 6) / 2;
+    const int cc_[6] = {22, 23, 23, 21, 21, 22};
+    const int ww_[6] = {2, 1, 0, 2, 1, 0};          // which of (w3, w4, w5) multiplies
+    const double dI[3] = {Iz - Iy, Ix - Iz, Iy - Ix};
+    int cc = 22, ww = 2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (lane % 6 == k) { cc = cc_[k]; ww = ww_[k]; }
+    gy_off = rr * LD + cc;
+    gy_w = ww;
+    gy_coef = -h * ((rr == 3) ? dI[0] : (rr == 4) ? dI[1] : dI[2]) * p[18 + rr];
+  }
+  // the angle whose sine / cosine this lane computes: x[ang_a] (+ x[ang_b] for hip + knee)
+  const int ang_a = (dp == 0) ? 6 + 3 * leg : (dp <= 2) ? 7 + 3 * leg : (dp == 3) ? 3 : (dp == 4) ? 4 : 5;
+  const int ang_b = 8 + 3 * leg;
+  const double ang_wb = (dp == 2) ? 1.0 : 0.0;
   const int stride = gridDim.x * kQfWarps;
   auto fetch_idx = [&](int it, int& bb, int& tt) -> bool {
     if (it >= n_items) return false;
@@ -146,12 +167,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       // hip + knee of their leg, dp = 3..5 roll, pitch, yaw (same values in every group)
       double sn, cs;
       {
-        const double ang = (dp == 0)   ? xin[6 + 3 * leg]
-                           : (dp == 1) ? xin[7 + 3 * leg]
-                           : (dp == 2) ? (xin[7 + 3 * leg] + xin[8 + 3 * leg])
-                           : (dp == 3) ? xin[3]
-                           : (dp == 4) ? xin[4]
-                                       : xin[5];
+        const double ang = xin[ang_a] + ang_wb * xin[ang_b];
         sincos_(ang, &sn, &cs);
       }
       const int gl = lane & ~7;   // first lane of this leg's group
@@ -268,19 +284,9 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         }
       }
       __syncwarp();
-      // gyroscopic terms of the base rotation rows (d/d omega of the omega x I omega term)
-      if (lane < 6) {
-        const int rr = 3 + lane / 2;
-        const int cc = (lane == 0) ? 22 : (lane == 1) ? 23 : (lane == 2) ? 23 : (lane == 3) ? 21 : (lane == 4) ? 21 : 22;
-        const double w3 = xin[21], w4 = xin[22], w5 = xin[23];
-        const double val = (lane == 0)   ? -h * (Iz - Iy) * w5 * p[21]
-                           : (lane == 1) ? -h * (Iz - Iy) * w4 * p[21]
-                           : (lane == 2) ? -h * (Ix - Iz) * w3 * p[22]
-                           : (lane == 3) ? -h * (Ix - Iz) * w5 * p[22]
-                           : (lane == 4) ? -h * (Iy - Ix) * w4 * p[23]
-                                         : -h * (Iy - Ix) * w3 * p[23];
-        Dv[rr * LD + cc] += val;
-      }
+      // gyroscopic terms of the base rotation rows (d/d omega of the omega x I omega term): entry
+      // (gy_off) += gy_coef * omega[gy_w], constants per lane (branch-free)
+      if (lane < 6) Dv[gy_off] += gy_coef * xin[21 + gy_w];
       __syncwarp();
       if (sub == 0) {
         if (nok) nxt = fetch_pt(nb, nt);   // next point's state and controls: consumed a substep later
@@ -304,9 +310,11 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       for (int idx = lane; idx < 18 * 18; idx += 32) {
         const int r = idx / 18, jc = idx - 18 * r;
         const double* row = s.D2v + r * LD;
-        double aqn = row[jc];
-        if (jc == 4) aqn = row[3] * N34 + row[4] * N44 + row[5] * N54;
-        if (jc == 5) aqn = row[3] * N35 + row[4] * N45 + row[5] * N55;
+        // (Aq N1)[r][jc]: N1 is the identity but for columns 4 and 5 (branch-free: weights per column)
+        const bool c4 = jc == 4, c5 = jc == 5;
+        const double k3 = c4 ? N34 : (c5 ? N35 : 0.0), k4 = c4 ? N44 : (c5 ? N45 : 0.0), k5 = c4 ? N54 : (c5 ? N55 : 0.0);
+        const double own = (c4 || c5) ? 0.0 : row[jc];
+        const double aqn = own + (row[3] * k3 + row[4] * k4 + row[5] * k5);
         s.D2v[r * LD + 18 + jc] = row[18 + jc] + h * aqn;
       }
       __syncwarp();

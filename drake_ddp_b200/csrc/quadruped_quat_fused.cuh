@@ -59,6 +59,27 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   for (int i = lane; i < 20 * LD; i += 32) s.Z[i] = 0.0;
   __syncwarp();
 
+  // per-lane constants of the gyroscopic entries (lanes 0..5): row 3 + lane / 2, column and angular
+  // velocity component by the cross-product pattern, coefficient -h (I_a - I_b) / I_row
+  int gy_off = 0, gy_w = 0;
+  double gy_coef = 0.0;
+  {
+    const int rr = 3 + (lane % 6) / 2;
+    const int cc_[6] = {22, 23, 23, 21, 21, 22};
+    const int ww_[6] = {2, 1, 0, 2, 1, 0};          // which of (w3, w4, w5) multiplies
+    const double dI[3] = {Iz - Iy, Ix - Iz, Iy - Ix};
+    int cc = 22, ww = 2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (lane % 6 == k) { cc = cc_[k]; ww = ww_[k]; }
+    gy_off = rr * LD + cc;
+    gy_w = ww;
+    gy_coef = -h * ((rr == 3) ? dI[0] : (rr == 4) ? dI[1] : dI[2]) * p[18 + rr];
+  }
+  // the angle whose sine / cosine this lane computes: x[ang_a] (+ x[ang_b] for hip + knee)
+  const int ang_a = (dp == 0) ? 7 + 3 * leg : 8 + 3 * leg;
+  const int ang_b = 9 + 3 * leg;
+  const double ang_wb = (dp >= 2) ? 1.0 : 0.0;
   const int stride = gridDim.x * kQfWarps;
   auto fetch_idx = [&](int it, int& bb, int& tt) -> bool {
     if (it >= n_items) return false;
@@ -124,7 +145,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       // ---- dual evaluation of this lane's leg along its two local directions ---------------------
       double sn, cs;
       {
-        const double ang = (dp == 0) ? xin[7 + 3 * leg] : (dp == 1) ? xin[8 + 3 * leg] : (xin[8 + 3 * leg] + xin[9 + 3 * leg]);
+        const double ang = xin[ang_a] + ang_wb * xin[ang_b];
         sincos_(ang, &sn, &cs);
       }
       const int gl = lane & ~7;   // first lane of this leg's group
@@ -244,18 +265,11 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         if (lane < 4) xout[lane] = (lane == 0) ? e0 : (lane == 1) ? e1 : (lane == 2) ? e2 : e3;
       }
       __syncwarp();
-      // gyroscopic terms of the body angular rows (d/d omega_body of the omega x I omega term)
-      if (lane < 6) {
-        const int rr = 3 + lane / 2;
-        const int cc = (lane == 0) ? 22 : (lane == 1) ? 23 : (lane == 2) ? 23 : (lane == 3) ? 21 : (lane == 4) ? 21 : 22;
-        const double w3 = vloc[3], w4 = vloc[4], w5 = vloc[5];
-        const double val = (lane == 0)   ? -h * (Iz - Iy) * w5 * p[21]
-                           : (lane == 1) ? -h * (Iz - Iy) * w4 * p[21]
-                           : (lane == 2) ? -h * (Ix - Iz) * w3 * p[22]
-                           : (lane == 3) ? -h * (Ix - Iz) * w5 * p[22]
-                           : (lane == 4) ? -h * (Iy - Ix) * w4 * p[23]
-                                         : -h * (Iy - Ix) * w3 * p[23];
-        Z[rr * LD + cc] += val;
+      // gyroscopic terms of the body angular rows (d/d omega_body of the omega x I omega term): entry
+      // (gy_off) += gy_coef * omega_body[gy_w], constants per lane (branch-free)
+      {
+        const double wsel = (gy_w == 0) ? vloc[3] : ((gy_w == 1) ? vloc[4] : vloc[5]);
+        if (lane < 6) Z[gy_off] += gy_coef * wsel;
       }
       __syncwarp();
       if (sub == 0) {

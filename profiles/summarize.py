@@ -86,8 +86,10 @@ def main():
     traffic = {}
     names = {"backward_sym": "backward_sym_kernel", "quad_fused": "quad_fused_kernel",
              "rollout_quad8": "rollout_quad8_kernel", "linearize": "linearize_kernel",
-             "rollout_arm8": "rollout_arm8_kernel", "rollout_quat": "rollout_quad8_kernel<QUAT>"}
-    for kern in ("backward_sym", "quad_fused", "linearize", "rollout_quad8", "rollout_arm8", "rollout_quat"):
+             "rollout_arm8": "rollout_arm8_kernel", "quad_quat_fused": "quad_quat_fused_kernel",
+             "backward_sym_n37": "backward_sym_kernel<QuadrupedQuat>"}
+    for kern in ("backward_sym", "quad_fused", "linearize", "rollout_quad8", "rollout_arm8", "quad_quat_fused",
+                 "backward_sym_n37"):
         rep = os.path.join(GO, f"prof_{kern}_{tag}.ncu-rep")
         if not os.path.exists(rep):
             continue
