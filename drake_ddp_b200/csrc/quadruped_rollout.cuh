@@ -185,6 +185,9 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
     const int r = lane + kRqLanes * k;
     wr[k] = (r < m) ? d.R[r * m + r] : 0.0;
   }
+  // reciprocal mass / inertia of the base acceleration this lane computes (lanes 0..5), fetched once:
+  // a ternary over global loads inside the step compiles to branches
+  const double rcp_l = (lane < 3) ? p[20] : (lane == 3) ? p[21] : (lane == 4) ? p[22] : p[23];
   double L = 0.0, E = 0.0;
   bool ok = true;
 #ifdef DDP_ROLL_PROFILE
@@ -354,8 +357,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
       if (!QUAT) {   // Quadruped::base_acc: [linear | body angular]
         const double num = (lane == 0) ? f[0] : (lane == 1) ? f[1] : (lane == 2) ? f[2] : (lane == 3) ? n3 : (lane == 4) ? n4 : n5;
-        const double rcp = (lane < 3) ? p[20] : (lane == 3) ? p[21] : (lane == 4) ? p[22] : p[23];
-        double a = num * rcp;
+        double a = num * rcp_l;
         if (lane == 2) a -= grav;
         if (lane < 6) s.acc[lane] = a;
       } else {       // QuadrupedQuat::step: [world angular = R (body angular) | linear]
