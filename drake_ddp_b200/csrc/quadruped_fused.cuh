@@ -182,7 +182,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
 #pragma unroll
         for (int e = 0; e < ND; ++e) {
           jd[e] = 2 * dp + pass * ND + e;
-          gc[e] = qf_gcol(leg, jd[e]);
+          gc[e] = qf_gcol(leg, jd[e]);   // (hoisting these two out of the point loop costs two registers: spills)
         }
         auto seed = [&](double v, int j) {
           D2 r;

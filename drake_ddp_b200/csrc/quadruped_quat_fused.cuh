@@ -80,6 +80,8 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   const int ang_a = (dp == 0) ? 7 + 3 * leg : 8 + 3 * leg;
   const int ang_b = 9 + 3 * leg;
   const double ang_wb = (dp >= 2) ? 1.0 : 0.0;
+  // columns in Z of this lane's two local directions (per-lane constants: qf_gcol branches)
+  const int gc_lane[2] = {qf_gcol(leg, 2 * dp), qf_gcol(leg, 2 * dp + 1)};
   const int stride = gridDim.x * kQfWarps;
   auto fetch_idx = [&](int it, int& bb, int& tt) -> bool {
     if (it >= n_items) return false;
@@ -155,7 +157,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           jd[e] = 2 * dp + e;
-          gc[e] = qf_gcol(leg, jd[e]);
+          gc[e] = gc_lane[e];
         }
         auto seed = [&](double v, int j) {
           D2 r;
