@@ -275,15 +275,23 @@ def timed_iterations(torch, solver, W, K, barrier, after_step=None):
     return e0.elapsed_time(e1), units, phase_ms, (t0, t1)
 
 
-def dominant(phase_ms, pb, active_per_step, K, ls_mean, hbm_peak, quad=True):
+KERNELS = {   # (line search, derivatives, backward sweep) kernels per model
+    "quadruped": ("rollout_quad8_kernel", "quad_fused_kernel", "backward_sym_kernel"),
+    "quadruped_quat": ("rollout_quad8_kernel<QUAT>", "quad_quat_fused_kernel", "backward_sym_kernel"),
+    "arm_ball": ("rollout_arm8_kernel", "linearize_kernel + interp_kernel", "backward_sym_kernel"),
+}
+
+
+def dominant(phase_ms, pb, active_per_step, K, ls_mean, hbm_peak, model="quadruped"):
     dom = max(phase_ms, key=phase_ms.get)
     launch_ms = phase_ms[dom] / K
+    names = KERNELS.get(model, ("rollout_kernel", "linearize_kernel", "backward_kernel"))
     if dom == "backward":
-        kernel, nbytes = "backward_sym_kernel", pb["backward"] * active_per_step
+        kernel, nbytes = names[2], pb["backward"] * active_per_step
     elif dom == "derivs":
-        kernel, nbytes = ("quad_fused_kernel" if quad else "linearize_kernel"), pb["derivs"] * active_per_step
+        kernel, nbytes = names[1], pb["derivs"] * active_per_step
     else:
-        kernel = ("rollout_quad8_kernel" if quad else "rollout_kernel") + " (line-search phase, all rounds)"
+        kernel = names[0] + " (line-search phase, all rounds)"
         nbytes = pb["rollout"] * active_per_step * ls_mean
     ach = nbytes / (launch_ms * 1e-3) / 1e9
     return {"kernel": kernel, "achieved": ach, "frac": ach / hbm_peak, "launch_ms": launch_ms,
@@ -326,7 +334,7 @@ def solve_batch_throughput(torch, prob, B, x0, A=None, max_iters=40, hbm_peak=65
     status = s.status
     ls_mean = float(np.mean(s.get_int(_lib.I_LS_ITERS)))
     pb = phase_bytes(n, m, N)
-    dom = dominant(ph, pb, units / iters, iters, ls_mean, hbm_peak, quad=False)
+    dom = dominant(ph, pb, units / iters, iters, ls_mean, hbm_peak, model=prob.system.name)
     out = {"n": n, "m": m, "N": N, "B": B, "ls_parallel": s.A, "value": units / (ms * 1e-3), "unit": UNIT,
            "batch_iterations": iters, "ms_per_batch_iteration": ms / iters,
            "mean_active_per_step": units / iters,
