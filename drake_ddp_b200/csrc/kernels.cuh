@@ -124,13 +124,56 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int pe
   double L = 0.0, E = 0.0;
   bool ok = true;
   int t = 0;
+  // Small models (n + m <= 8, one lane per candidate): a step is a few dozen flops, so the global
+  // loads of its operands (K_t, x_bar_t, u_bar_t, kappa_t, dV_t: L2 latency) would be most of it.
+  // They are fetched one step ahead into registers (m n + n + 2 m + 1 doubles).
+  constexpr bool PRE = Cfg<Model>::small && G == 1;
+  double nK[PRE ? m * n : 1], nxb[PRE ? n : 1], nub[PRE ? m : 1], nkp[PRE ? m : 1], ndv = 0.0;
+  auto prefetch_step = [&](int tt) {
+    if constexpr (PRE) {
+      const double* gK = d.K + ((size_t)b * T + tt) * m * n;
+      const double* gx = d.x_bar + ((size_t)b * N + tt) * n;
+      const double* gu = d.u_bar + ((size_t)b * T + tt) * m;
+      const double* gk = d.kappa + ((size_t)b * T + tt) * m;
+#pragma unroll
+      for (int i = 0; i < m * n; ++i) nK[i] = gK[i];
+#pragma unroll
+      for (int i = 0; i < n; ++i) nxb[i] = gx[i];
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+        nub[i] = gu[i];
+        nkp[i] = gk[i];
+      }
+      ndv = d.dV[(size_t)b * T + tt];
+    }
+  };
+  prefetch_step(0);
   for (; t < T; ++t) {
+    double cK[PRE ? m * n : 1], cxb[PRE ? n : 1], cub[PRE ? m : 1], ckp[PRE ? m : 1], cdv = 0.0;
+    if constexpr (PRE) {
+#pragma unroll
+      for (int i = 0; i < m * n; ++i) cK[i] = nK[i];
+#pragma unroll
+      for (int i = 0; i < n; ++i) cxb[i] = nxb[i];
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+        cub[i] = nub[i];
+        ckp[i] = nkp[i];
+      }
+      cdv = ndv;
+      if (t + 1 < T) prefetch_step(t + 1);
+    }
     const double* Kt = d.K + ((size_t)b * T + t) * m * n;
     const double* xb = d.x_bar + ((size_t)b * N + t) * n;
     const double* ub = d.u_bar + ((size_t)b * T + t) * m;
     const double* kp = d.kappa + ((size_t)b * T + t) * m;
+    // operand accessors: the register copies (compile-time indices after unrolling) or global memory
+    auto opK = [&](int i) { if constexpr (PRE) return cK[i]; else return Kt[i]; };
+    auto opX = [&](int j) { if constexpr (PRE) return cxb[j]; else return xb[j]; };
+    auto opU = [&](int r) { if constexpr (PRE) return cub[r]; else return ub[r]; };
+    auto opP = [&](int r) { if constexpr (PRE) return ckp[r]; else return kp[r]; };
     // pull the next step's gain rows towards L2/L1 while this step computes
-    if (t + 1 < T) {
+    if (!PRE && t + 1 < T) {
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
         const int r = lane + G * i;
@@ -144,17 +187,16 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int pe
     // u_t = u_bar_t - eps*kappa_t - K_t (x_t - x_bar_t)            (ilqr.py:313)
     double dx[n];
 #pragma unroll
-    for (int j = 0; j < n; ++j) dx[j] = x[j] - xb[j];
+    for (int j = 0; j < n; ++j) dx[j] = x[j] - opX(j);
     double mine[RPL];
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const int r = lane + G * i;
       double acc = 0.0;
       if (r < m) {
-        const double* Kr = Kt + (size_t)r * n;
 #pragma unroll
-        for (int j = 0; j < n; ++j) acc = fma(Kr[j], dx[j], acc);
-        acc = ub[r] - eps * kp[r] - acc;
+        for (int j = 0; j < n; ++j) acc = fma(opK(r * n + j), dx[j], acc);
+        acc = opU(r) - eps * opP(r) - acc;
         if (d.u_min) acc = fmin(fmax(acc, d.u_min[r]), d.u_max[r]);   // extension, off by default
       }
       mine[i] = acc;
@@ -201,7 +243,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int pe
       }
       L += s;
     }
-    E += ecoef * d.dV[(size_t)b * T + t];                      //  (ilqr.py:326)
+    E += ecoef * (PRE ? cdv : d.dV[(size_t)b * T + t]);        //  (ilqr.py:326)
 #pragma unroll
     for (int r = 0; r < m; ++r)
       if (r % G == lane) uo[(size_t)t * m + r] = u[r];
@@ -655,6 +697,7 @@ struct BwdSmem {
   double Quu[m * m], Inv[m * m];
   double Vx[n], Qx[n], xb[n];
   double Qu[m], g[m], kap[m], ub[m];
+  double Q2[n * n], R2[m * m];   // 2 Q, 2 R (lxx, luu), read once
 };
 
 // explicit inverse of the m x m matrix A into Inv: in-place Gauss-Jordan with partial pivoting,
@@ -734,14 +777,42 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
   }
   __syncthreads();
 
+  // The tiles of a step (fx, fu, x_bar, u_bar) are fetched one step ahead into registers (each
+  // thread its own elements): for these small shapes a step is a few hundred flops and the L2
+  // latency of a blocking load would be a third of it.
+  constexpr int PFX = (n * n + NT - 1) / NT, PFU = (n * m + NT - 1) / NT, PX = (n + NT - 1) / NT, PU = (m + NT - 1) / NT;
+  double pfx[PFX], pfu[PFU], pxb[PX], pub[PU];
+  auto fetch_tiles = [&](int tt) {
+    const double* gfx = d.fx + ((size_t)b * T + tt) * n * n;
+    const double* gfu = d.fu + ((size_t)b * T + tt) * n * m;
+#pragma unroll
+    for (int k = 0; k < PFX; ++k) pfx[k] = (tid + k * NT < n * n) ? gfx[tid + k * NT] : 0.0;
+#pragma unroll
+    for (int k = 0; k < PFU; ++k) pfu[k] = (tid + k * NT < n * m) ? gfu[tid + k * NT] : 0.0;
+#pragma unroll
+    for (int k = 0; k < PX; ++k) pxb[k] = (tid + k * NT < n) ? d.x_bar[((size_t)b * N + tt) * n + tid + k * NT] : 0.0;
+#pragma unroll
+    for (int k = 0; k < PU; ++k) pub[k] = (tid + k * NT < m) ? d.u_bar[((size_t)b * T + tt) * m + tid + k * NT] : 0.0;
+  };
+  fetch_tiles(T - 1);
+  for (int i = tid; i < n * n; i += NT) s.Q2[i] = 2.0 * Q[i];
+  for (int i = tid; i < m * m; i += NT) s.R2[i] = 2.0 * R[i];
+
   for (int t = T - 1; t >= 0; --t) {
-    const double* gfx = d.fx + ((size_t)b * T + t) * n * n;
-    const double* gfu = d.fu + ((size_t)b * T + t) * n * m;
-    for (int i = tid; i < n * n; i += NT) s.Fx[i] = gfx[i];
-    for (int i = tid; i < n * m; i += NT) s.Fu[i] = gfu[i];
-    for (int i = tid; i < n; i += NT) s.xb[i] = d.x_bar[((size_t)b * N + t) * n + i];
-    for (int i = tid; i < m; i += NT) s.ub[i] = d.u_bar[((size_t)b * T + t) * m + i];
+#pragma unroll
+    for (int k = 0; k < PFX; ++k)
+      if (tid + k * NT < n * n) s.Fx[tid + k * NT] = pfx[k];
+#pragma unroll
+    for (int k = 0; k < PFU; ++k)
+      if (tid + k * NT < n * m) s.Fu[tid + k * NT] = pfu[k];
+#pragma unroll
+    for (int k = 0; k < PX; ++k)
+      if (tid + k * NT < n) s.xb[tid + k * NT] = pxb[k];
+#pragma unroll
+    for (int k = 0; k < PU; ++k)
+      if (tid + k * NT < m) s.ub[tid + k * NT] = pub[k];
     __syncthreads();
+    if (t > 0) fetch_tiles(t - 1);   // consumed at the top of the next step
     // W = Vxx fx, Wu = Vxx fu
     for (int idx = tid; idx < n * n; idx += NT) {
       const int i = idx / n, k = idx % n;
@@ -761,11 +832,11 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
     for (int k = tid; k < n; k += NT) {
       double a = 0.0, c = 0.0;
       if (d.diag_cost) {
-        a = 2.0 * Q[k * n + k] * s.xb[k];
+        a = s.Q2[k * n + k] * s.xb[k];
         c = 2.0 * xnom[k] * Q[k * n + k];
       } else {
         for (int j = 0; j < n; ++j) {
-          a = fma(2.0 * Q[k * n + j], s.xb[j], a);
+          a = fma(s.Q2[k * n + j], s.xb[j], a);
           c = fma(2.0 * xnom[j], Q[j * n + k], c);
         }
       }
@@ -775,7 +846,7 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
     }
     for (int r = tid; r < m; r += NT) {
       double a = 0.0;
-      for (int j = 0; j < m; ++j) a = fma(2.0 * R[r * m + j], s.ub[j], a);
+      for (int j = 0; j < m; ++j) a = fma(s.R2[r * m + j], s.ub[j], a);
       for (int i = 0; i < n; ++i) a = fma(s.Fu[i * m + r], s.Vx[i], a);
       s.Qu[r] = a;
     }
@@ -783,7 +854,7 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
     // Qxx = lxx + fx' W (into Vxx) ; Qux = fu' W ; Quu = luu + fu' Wu   (ilqr.py:653-656)
     for (int idx = tid; idx < n * n; idx += NT) {
       const int k = idx / n, l = idx % n;
-      double a = 2.0 * Q[idx];
+      double a = s.Q2[idx];
 #pragma unroll 4
       for (int i = 0; i < n; ++i) a = fma(s.Fx[i * n + k], s.W[i * n + l], a);
       s.Vxx[idx] = a;
@@ -797,12 +868,16 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
     }
     for (int idx = tid; idx < m * m; idx += NT) {
       const int r = idx / m, q = idx % m;
-      double a = 2.0 * R[idx];
+      double a = s.R2[idx];
       for (int i = 0; i < n; ++i) a = fma(s.Fu[i * m + r], s.Wu[i * m + q], a);
       s.Quu[idx] = (r == q) ? a + d.quu_reg : a;
     }
     __syncthreads();
-    if (tid < 32) invert_warp<m>(s.Quu, s.Inv);                 // ilqr.py:655
+    if constexpr (m == 1) {                                      // ilqr.py:655
+      if (tid == 0) s.Inv[0] = 1.0 / s.Quu[0];                   // what the pivoting inverse does for a scalar
+    } else {
+      if (tid < 32) invert_warp<m>(s.Quu, s.Inv);
+    }
     __syncthreads();
     // kappa = Quu^-1 Qu ; K = Quu^-1 Qux ; g = Qu' Quu^-1          (ilqr.py:659-663)
     for (int r = tid; r < m; r += NT) {
