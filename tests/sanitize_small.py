@@ -1,7 +1,8 @@
 """Tiny end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): two iLQR iterations
 of small quadruped (fused linearization, 8-lane rollout, symmetric backward sweep), quadruped_quat
-(generic kernels, cp.async backward path) and pendulum (scalar backward kernel) problems, with the
-device-side MPC re-arm on.  Driven by tests/test_gpu_parity.py::test_compute_sanitizer_clean_..."""
+(the same three in the n = 37 layout: odd-sized bulk-TMA tiles, single fx buffer), arm_ball (8-lane
+arm rollout, generic AD + interpolation, odd-sized tiles) and pendulum (scalar kernels) problems,
+with the device-side MPC re-arm on.  Driven by tests/test_gpu_parity.py::test_compute_sanitizer_clean_..."""
 import os
 import sys
 
@@ -9,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from drake_ddp_b200 import problems
 from drake_ddp_b200.ilqr import BatchedILQR
 
-for name, N in (("quadruped", 12), ("quadruped_quat", 10), ("pendulum", 20)):
+for name, N in (("quadruped", 12), ("quadruped_quat", 10), ("arm_ball", 10), ("pendulum", 20)):
     prob = getattr(problems, name)(N)
     B = 3
     s = BatchedILQR(prob.system, prob.N, batch=B, delta=prob.delta, beta=prob.beta, gamma=prob.gamma,
