@@ -354,7 +354,8 @@ int phase_derivatives(ddp_solver* s) {
     if (rc) return rc;
   }
   if (!(d.kp_method == DDP_KP_SET_INTERVAL && d.minN == 1)) {
-    LAUNCH1(segments_kernel, d);
+    segments_kernel<<<d.B, 128, 0, s->stream>>>(d);
+    s->launches++;
     interp_kernel<<<(unsigned)((size_t)d.B * d.T), 128, 0, s->stream>>>(d);
     s->launches++;
   }
