@@ -381,7 +381,7 @@ int iterate_finish_impl(ddp_solver* s) {
   CK(cudaEventRecord(s->ev[3], s->stream));
   LAUNCH1(finish_iter_kernel, d);
   if (d.mpc_replan > 0) {
-    mpc_rearm_kernel<<<d.B, 64, 0, s->stream>>>(d);
+    mpc_rearm_kernel<<<d.B, 256, 0, s->stream>>>(d);
     s->launches++;
   }
   s->timings_valid = true;

@@ -354,9 +354,22 @@ __global__ void mpc_shift_kernel(Dev d, int r) {
   const int b = blockIdx.x;
   const int m = d.m, T = d.T, n = d.n;
   double* u = d.u_bar + (size_t)b * T * m;
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    const double last = u[(size_t)(T - 1) * m + j];
-    for (int t = 0; t < T; ++t) u[(size_t)t * m + j] = (t + r < T) ? u[(size_t)(t + r) * m + j] : last;
+  {
+    // in-place shift of the [T][m] tape by r rows, all threads: chunks of blockDim elements in
+    // increasing order; a chunk's sources lie at or after its own destinations, so "read all, sync,
+    // write all" per chunk never loses a value.  Rows t >= T - r repeat the (original) last row.
+    __shared__ double last[32];
+    for (int j = threadIdx.x; j < m; j += blockDim.x) last[j] = u[(size_t)(T - 1) * m + j];
+    __syncthreads();
+    const int total = T * m, shift = r * m;
+    for (int base = 0; base < total; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      double v = 0.0;
+      if (i < total) v = (i + shift < total) ? u[i + shift] : last[i % m];
+      __syncthreads();
+      if (i < total) u[i] = v;
+      __syncthreads();
+    }
   }
   double* x0 = const_cast<double*>(d.x0) + (size_t)b * n;
   const double* xr = d.x_bar + ((size_t)b * d.N + r) * n;
@@ -372,9 +385,22 @@ __global__ void mpc_rearm_kernel(Dev d) {
   if (!d.rearm[b]) return;
   const int m = d.m, T = d.T, n = d.n, r = d.mpc_replan;
   double* u = d.u_bar + (size_t)b * T * m;
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    const double last = u[(size_t)(T - 1) * m + j];
-    for (int t = 0; t < T; ++t) u[(size_t)t * m + j] = (t + r < T) ? u[(size_t)(t + r) * m + j] : last;
+  {
+    // in-place shift of the [T][m] tape by r rows, all threads: chunks of blockDim elements in
+    // increasing order; a chunk's sources lie at or after its own destinations, so "read all, sync,
+    // write all" per chunk never loses a value.  Rows t >= T - r repeat the (original) last row.
+    __shared__ double last[32];
+    for (int j = threadIdx.x; j < m; j += blockDim.x) last[j] = u[(size_t)(T - 1) * m + j];
+    __syncthreads();
+    const int total = T * m, shift = r * m;
+    for (int base = 0; base < total; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      double v = 0.0;
+      if (i < total) v = (i + shift < total) ? u[i + shift] : last[i % m];
+      __syncthreads();
+      if (i < total) u[i] = v;
+      __syncthreads();
+    }
   }
   double* x0 = const_cast<double*>(d.x0) + (size_t)b * n;
   double* xnom = const_cast<double*>(d.x_nom) + (size_t)b * n;
