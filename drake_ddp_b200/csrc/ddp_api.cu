@@ -324,7 +324,8 @@ int phase_derivatives(ddp_solver* s) {
   Dev& d = s->d;
   int rc = 0;
   if (d.kp_method == DDP_KP_SET_INTERVAL) {
-    LAUNCH1(kp_set_interval_kernel, d);
+    kp_set_interval_kernel<<<d.B, 128, 0, s->stream>>>(d);
+    s->launches++;
   } else if (d.kp_method == DDP_KP_ADAPTIVE_JERK) {
     if (d.N > 3) {
       jerk_flag_kernel<<<cdiv((size_t)d.B * (d.N - 3), 128), 128, 0, s->stream>>>(d);

@@ -480,14 +480,15 @@ __global__ void finish_iter_kernel(Dev d) {
 // K3  keypoint selection (ilqr.py:417-539) -> ascending list per trajectory.
 // =============================================================================================
 // get_keypoints_set_interval, ilqr.py:417-432
+// (CTA per trajectory, a thread per keypoint: the list is written coalesced)
 __global__ void kp_set_interval_kernel(Dev d) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= d.B || !d.active[b]) return;
+  const int b = blockIdx.x;
+  if (!d.active[b]) return;
   int* list = d.kplist + (size_t)b * d.T;
-  int cnt = 0;
-  for (int t = 0; t < d.N - 1; t += d.minN) list[cnt++] = t;
-  if (list[cnt - 1] != d.N - 2) list[cnt - 1] = d.N - 2;
-  d.kpcount[b] = cnt;
+  const int cnt = (d.N - 2) / d.minN + 1;           // t = 0, minN, 2 minN, ... < N - 1
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+    list[i] = (i == cnt - 1) ? d.N - 2 : i * d.minN;   // the last keypoint is replaced by N - 2 (:428-430)
+  if (threadIdx.x == 0) d.kpcount[b] = cnt;
 }
 // calc_jerk_profile + threshold test, ilqr.py:470-486,454-455: flag[b][t] = any_i jerk[t,i] > thr
 __global__ void jerk_flag_kernel(Dev d) {
