@@ -595,8 +595,7 @@ def test_compute_sanitizer_clean_on_a_whole_iteration():
     for tool in ("memcheck", "synccheck", "racecheck"):
         env = dict(os.environ)
         if tool != "memcheck":
-            assert os.path.exists(_lib.RACECHECK_LIB_PATH), "build() compiles the sanitizer variant"
-            env["DDP_B200_LIB"] = _lib.RACECHECK_LIB_PATH
+            env["DDP_B200_LIB"] = _lib.build_racecheck()      # built by build(); compiled here if it did not travel
         r = subprocess.run([exe, "--tool", tool, "--error-exitcode", "7", sys.executable,
                             os.path.join(root, "tests", "sanitize_small.py")],
                            capture_output=True, text=True, timeout=900, cwd=root, env=env)
