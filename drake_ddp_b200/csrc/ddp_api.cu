@@ -46,6 +46,7 @@ struct ddp_solver {
   long long launches;
   bool timings_valid;
   bool scalar_backward;  // debug: force the scalar shared-memory kernel for n >= 16
+  bool small_backward;   // n <= 4, m = 1: thread-per-trajectory register kernel (DDP_SMALL_BACKWARD=cta: the CTA kernel)
   bool quad_rollout8;    // 8-lane quadruped rollout (DDP_QUAD_ROLLOUT=generic selects rollout_kernel)
   bool quad_fused;       // fused structured quadruped linearization (DDP_QUAD_LINEARIZE=fused|ad)
   bool arm_rollout8;     // 8-lane arm + ball rollout (DDP_ARM_ROLLOUT=generic selects rollout_kernel)
@@ -188,6 +189,16 @@ template <class Model>
 int launch_backward(ddp_solver* s) {
   if constexpr (Model::n >= 16) {
     if (!s->scalar_backward) return launch_backward_sym<Model>(s);
+  }
+  if constexpr (Model::n <= 4 && Model::m == 1) {
+    // thread per trajectory, everything in registers: wins for a handful of trajectories (the drop-in
+    // class: B = 1; pendulum 129 -> 63 us, cart-pole 243 -> 180 us per sweep); at B = 50 its per-thread
+    // tile loads are 32 uncoalesced streams per warp and the CTA kernel is faster (455 vs 503 us)
+    if (s->small_backward && s->d.B <= 8) {
+      backward_small_kernel<Model><<<cdiv(s->d.B, 32), 32, 0, s->stream>>>(s->d);
+      s->launches++;
+      return 0;
+    }
   }
   constexpr int NT = Cfg<Model>::BWD_THREADS;
   const size_t smem = sizeof(BwdSmem<Model::n, Model::m>);
@@ -503,6 +514,10 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   s->h_counters = nullptr;
   for (int i = 0; i < 4; ++i) s->ev[i] = nullptr;
   s->scalar_backward = getenv("DDP_SCALAR_BACKWARD") != nullptr;
+  {
+    const char* sb = getenv("DDP_SMALL_BACKWARD");
+    s->small_backward = !(sb && std::string(sb) == "cta");
+  }
   Dev& d = s->d;
   d.n = n; d.m = m; d.N = N; d.T = N - 1; d.B = B; d.A = A;
   Carver c{(char*)workspace_dev, 0};

@@ -959,6 +959,156 @@ __global__ void __launch_bounds__(NT) backward_kernel(Dev d) {
 }
 
 // =============================================================================================
+// K6 for the smallest models (n <= 4, m = 1: pendulum, acrobot, cart-pole): the same sweep with a
+// THREAD per trajectory and every matrix in registers.  A step is ~40-250 flops: the CTA version
+// above spends most of its microsecond per step on seven barriers and shared-memory round trips
+// between phases of a handful of operations each.  Same formulas and the same order of operations
+// as backward_kernel (results are bit-identical); the next step's tiles are pulled towards L1
+// while the current step computes.  Used for B <= 8 (per-thread tile loads do not coalesce across
+// trajectories); DDP_SMALL_BACKWARD=cta selects the CTA kernel.
+// =============================================================================================
+template <class Model>
+__global__ void __launch_bounds__(32) backward_small_kernel(Dev d) {
+  constexpr int n = Model::n, m = Model::m;
+  static_assert(n <= 4 && m == 1, "register-resident sweep: n <= 4, scalar control");
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || !d.active[b]) return;
+  const int N = d.N, T = d.T;
+  const double* Q = d.Q;
+  const double* Qf = d.Qf;
+  const double* xnom = d.x_nom + (size_t)b * n;
+  const double R2 = 2.0 * d.R[0];
+  const bool diag = d.diag_cost != 0;
+  double Q2[n][n], xn[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    xn[i] = xnom[i];
+#pragma unroll
+    for (int j = 0; j < n; ++j) Q2[i][j] = 2.0 * Q[i * n + j];
+  }
+  // Vx, Vxx <- terminal cost partials at x_bar[:, -1]            (ilqr.py:638, 203-204)
+  double Vxx[n][n], Vx[n];
+  {
+    const double* xl = d.x_bar + ((size_t)b * N + (N - 1)) * n;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double a = 0.0, c = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        Vxx[i][j] = 2.0 * Qf[i * n + j];
+        a = fma(2.0 * Qf[i * n + j], xl[j], a);
+        c = fma(2.0 * xn[j], Qf[j * n + i], c);
+      }
+      Vx[i] = a - c;
+    }
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    const double* gfx = d.fx + ((size_t)b * T + t) * n * n;
+    const double* gfu = d.fu + ((size_t)b * T + t) * n * m;
+    const double* gxb = d.x_bar + ((size_t)b * N + t) * n;
+    double fx[n][n], fu[n], xb[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      fu[i] = gfu[i];
+      xb[i] = gxb[i];
+#pragma unroll
+      for (int j = 0; j < n; ++j) fx[i][j] = gfx[i * n + j];
+    }
+    const double ub = d.u_bar[(size_t)b * T + t];
+    if (t > 0) {   // next step's tiles towards L1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gfx - n * n));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gfu - n));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gxb - n));
+    }
+    // W = Vxx fx, Wu = Vxx fu
+    double W[n][n], Wu[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int k = 0; k < n; ++k) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) a = fma(Vxx[i][j], fx[j][k], a);
+        W[i][k] = a;
+      }
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) a = fma(Vxx[i][j], fu[j], a);
+      Wu[i] = a;
+    }
+    // Qx = lx + fx' Vx ; Qu = lu + fu' Vx                         (ilqr.py:651-652,180-181)
+    double Qx[n], Qu;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      double a = 0.0, c = 0.0;
+      if (diag) {
+        a = Q2[k][k] * xb[k];
+        c = 2.0 * xn[k] * Q[k * n + k];
+      } else {
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+          a = fma(Q2[k][j], xb[j], a);
+          c = fma(2.0 * xn[j], Q[j * n + k], c);
+        }
+      }
+      double q = a - c;
+#pragma unroll
+      for (int i = 0; i < n; ++i) q = fma(fx[i][k], Vx[i], q);
+      Qx[k] = q;
+    }
+    {
+      double a = 0.0;
+      a = fma(R2, ub, a);
+#pragma unroll
+      for (int i = 0; i < n; ++i) a = fma(fu[i], Vx[i], a);
+      Qu = a;
+    }
+    // Qxx = lxx + fx' W (into Vxx) ; Qux = fu' W ; Quu = luu + fu' Wu   (ilqr.py:653-656)
+    double Qux[n], Quu;
+#pragma unroll
+    for (int k = 0; k < n; ++k)
+#pragma unroll
+      for (int l = 0; l < n; ++l) {
+        double a = Q2[k][l];
+#pragma unroll
+        for (int i = 0; i < n; ++i) a = fma(fx[i][k], W[i][l], a);
+        Vxx[k][l] = a;
+      }
+#pragma unroll
+    for (int l = 0; l < n; ++l) {
+      double a = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) a = fma(fu[i], W[i][l], a);
+      Qux[l] = a;
+    }
+    {
+      double a = R2;
+#pragma unroll
+      for (int i = 0; i < n; ++i) a = fma(fu[i], Wu[i], a);
+      Quu = a + d.quu_reg;
+    }
+    const double Inv = 1.0 / Quu;                                  // ilqr.py:655
+    // kappa = Quu^-1 Qu ; K = Quu^-1 Qux ; g = Qu' Quu^-1 ; dV = g Qu      (ilqr.py:659-663)
+    const double kap = fma(Inv, Qu, 0.0), g = fma(Qu, Inv, 0.0);
+    double Kt[n];
+#pragma unroll
+    for (int l = 0; l < n; ++l) Kt[l] = fma(Inv, Qux[l], 0.0);
+    double* gK = d.K + ((size_t)b * T + t) * m * n;
+#pragma unroll
+    for (int l = 0; l < n; ++l) gK[l] = Kt[l];
+    d.kappa[(size_t)b * T + t] = kap;
+    d.dV[(size_t)b * T + t] = fma(g, Qu, 0.0);
+    // Vx = Qx - g Qux ; Vxx = Qxx - Qux' K                          (ilqr.py:666-667)
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      Vx[k] = Qx[k] - fma(g, Qux[k], 0.0);
+#pragma unroll
+      for (int l = 0; l < n; ++l) Vxx[k][l] -= fma(Qux[k], Kt[l], 0.0);
+    }
+  }
+}
+
+// =============================================================================================
 // fp64 pipe microbenchmarks (bench.py states the fp64 roofline next to the HBM one)
 // =============================================================================================
 __global__ void peak_dfma_kernel(double* out, int iters) {

@@ -458,6 +458,28 @@ def test_arm_rollout8_matches_generic_rollout(monkeypatch):
     assert relerr(q[5], g[5]) < 1e-9
 
 
+@pytest.mark.parametrize("name", ["pendulum", "acrobot", "cart_pole_with_wall"])
+def test_small_backward_register_kernel_equals_cta_kernel(monkeypatch, name):
+    """backward_small_kernel (n <= 4, m = 1: a thread per trajectory, matrices in registers) against
+    the CTA kernel (DDP_SMALL_BACKWARD=cta): same formulas in the same order, so K, kappa, dV and the
+    costs of the following iterations are bit-identical."""
+    prob = getattr(problems, name)(60)
+    B = 5                                    # the register kernel is used up to B = 8
+    x0 = prob.batch_x0(B, seed=4)
+    out = {}
+    for mode in ("reg", "cta"):
+        monkeypatch.delenv("DDP_SMALL_BACKWARD", raising=False)
+        if mode == "cta":
+            monkeypatch.setenv("DDP_SMALL_BACKWARD", "cta")
+        s = make_gpu(prob, B=B, x0=x0)
+        s.begin_solve()
+        for _ in range(4):
+            s.iterate()
+        out[mode] = (s.get(_lib.K), s.get(_lib.KAPPA), s.get(_lib.DV), s.cost.copy())
+    for a, b in zip(out["reg"], out["cta"]):
+        assert np.array_equal(a, b)
+
+
 def test_split_iterate_and_host_exchange_equal_iterate():
     """ddp_iterate_linesearch / _finish_async / _wait with the overlapped host exchange
     (HostExchange: staged upload, control read-back under the backward pass) give bit-identical
