@@ -174,7 +174,14 @@ struct BsCfg {
   static constexpr int MAXS = bs_max3(SD.cnt[0], SD.cnt[1], SD.cnt[2]);
   static constexpr BsDeal KD = bs_deal(TN, TM);   // column strips of K (K_c and its update tiles)
   static constexpr int MAXK = bs_max3(KD.cnt[0], KD.cnt[1], KD.cnt[2]);
-  static constexpr int LDV = n;                   // leading dimension of Vxx in shared memory
+  // leading dimension of Vxx in shared memory: the A-operand fetch of the W product reads rows g,
+  // columns 4 kk + tg; a half-warp (g = 0..3) is conflict-free when the row stride is 8 banks mod 32,
+  // i.e. LDV = 4 mod 16 doubles: 36 as it is, 37 -> 52, 27 -> 36 (DDP_BWD_LDV_PLAIN: LDV = n)
+#ifdef DDP_BWD_LDV_PLAIN
+  static constexpr int LDV = n;
+#else
+  static constexpr int LDV = (n % 16 == 4) ? n : ((n + 11) / 16) * 16 + 4;
+#endif
 #ifndef DDP_BWD_MINB
 #define DDP_BWD_MINB 4
 #endif
