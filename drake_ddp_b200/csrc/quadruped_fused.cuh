@@ -301,48 +301,41 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
     // so the position rows of D1 are never formed and the product has K = 18: 90 DMMAs.
     // M1 and N1 differ from the identity only in rows / columns 3..5 (roll, pitch, yaw).
     const double* D1v = s.D1v;
-    {
-      const double sr = trig[0][0], cr = trig[0][1], sp = trig[0][2], cp = trig[0][3];
-      const double icp = 1.0 / cp, tp = sp * icp, w4 = s.st[1][22], w5 = s.st[1][23];
-      const double wyz = sr * w4 + cr * w5, wr = cr * w4 - sr * w5;
-      const double N34 = tp * sr, N35 = tp * cr, N44 = cr, N45 = -sr, N54 = sr * icp, N55 = cr * icp;
-      // A' = Av + h Aq N1, in place of Av
-      for (int idx = lane; idx < 18 * 18; idx += 32) {
-        const int r = idx / 18, jc = idx - 18 * r;
-        const double* row = s.D2v + r * LD;
-        // (Aq N1)[r][jc]: N1 is the identity but for columns 4 and 5 (branch-free: weights per column)
-        const bool c4 = jc == 4, c5 = jc == 5;
-        const double k3 = c4 ? N34 : (c5 ? N35 : 0.0), k4 = c4 ? N44 : (c5 ? N45 : 0.0), k5 = c4 ? N54 : (c5 ? N55 : 0.0);
-        const double own = (c4 || c5) ? 0.0 : row[jc];
-        const double aqn = own + (row[3] * k3 + row[4] * k4 + row[5] * k5);
-        s.D2v[r * LD + 18 + jc] = row[18 + jc] + h * aqn;
-      }
-      __syncwarp();
-      // Aq E1, in place of Aq (columns 3 and 4 only)
-      if (lane < 18) {
-        double* row = s.D2v + lane * LD;
-        const double a3 = row[3], a4 = row[4], a5 = row[5];
-        row[3] = a3 * (1.0 + h * tp * wr) + a4 * (-h * wyz) + a5 * (h * wr * icp);
-        row[4] = a3 * (h * wyz * (icp * icp)) + a4 + a5 * (h * wyz * sp * (icp * icp));
-      }
-      __syncwarp();
-    }
+    // A' = Av + h Aq N1 is formed in the A-operand fetch of the product (N1 is the identity but for
+    // columns 4 and 5, which sit in k-step kk = 1 on lanes tg = 0, 1: per-lane weights, branch-free);
+    // Aq E1 then replaces Aq in place (columns 3 and 4 only) for the epilogue.
+    const double sr0 = trig[0][0], cr0 = trig[0][1], sp0 = trig[0][2], cp0 = trig[0][3];
+    const double icp0 = 1.0 / cp0, tp0 = sp0 * icp0, w40 = s.st[1][22], w50 = s.st[1][23];
+    const double wyz0 = sr0 * w40 + cr0 * w50, wr0 = cr0 * w40 - sr0 * w50;
     double acc[3][6][2];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 6; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     {
-      const double* pa[3];
+      const double N34 = tp0 * sr0, N35 = tp0 * cr0, N44 = cr0, N45 = -sr0, N54 = sr0 * icp0, N55 = cr0 * icp0;
+      const bool c4 = tg == 0, c5 = tg == 1;      // in k-step 1: column 4 + tg
+      const double k3 = c4 ? N34 : (c5 ? N35 : 0.0), k4 = c4 ? N44 : (c5 ? N45 : 0.0), k5 = c4 ? N54 : (c5 ? N55 : 0.0);
+      const double* pq[3];   // row of [Aq | Av | Au] of this lane's A-fragment row
 #pragma unroll
-      for (int mt = 0; mt < 3; ++mt) pa[mt] = s.D2v + min(8 * mt + g, 17) * LD + 18 + tg;
+      for (int mt = 0; mt < 3; ++mt) pq[mt] = s.D2v + min(8 * mt + g, 17) * LD;
       const double* pb = D1v + tg * LD + g;
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) {
         const bool kin = (kk < 4) || (tg < 2);   // k = 4 kk + tg < 18
         double a[3], bb[6];
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt) a[mt] = kin ? pa[mt][4 * kk] : 0.0;
+        for (int mt = 0; mt < 3; ++mt) {
+          const double* row = pq[mt];
+          double aqn;
+          if (kk == 1) {
+            const double own = (c4 || c5) ? 0.0 : row[4 + tg];
+            aqn = own + (row[3] * k3 + row[4] * k4 + row[5] * k5);
+          } else {
+            aqn = kin ? row[4 * kk + tg] : 0.0;
+          }
+          a[mt] = kin ? (row[18 + 4 * kk + tg] + h * aqn) : 0.0;
+        }
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) bb[nt] = kin ? pb[4 * kk * LD + 8 * nt] : 0.0;
 #pragma unroll
@@ -350,6 +343,15 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
 #pragma unroll
           for (int nt = 0; nt < 6; ++nt) dmma(acc[mt][nt], a[mt], bb[nt]);
       }
+      __syncwarp();   // every fetch of Aq done
+      // Aq E1, in place of Aq (columns 3 and 4 only)
+      if (lane < 18) {
+        double* row = s.D2v + lane * LD;
+        const double a3 = row[3], a4 = row[4], a5 = row[5];
+        row[3] = a3 * (1.0 + h * tp0 * wr0) + a4 * (-h * wyz0) + a5 * (h * wr0 * icp0);
+        row[4] = a3 * (h * wyz0 * (icp0 * icp0)) + a4 + a5 * (h * wyz0 * sp0 * (icp0 * icp0));
+      }
+      __syncwarp();
     }
     double* fx = d.fx + bt * 36 * 36;
     double* fu = d.fu + bt * 36 * 12;
