@@ -389,8 +389,9 @@ __device__ __forceinline__ void bs_route(BsSmem<n, m>& s, const BsCtx<n, m>& x, 
     if (VXX) {
       if (x.diag) v += (i == j) ? s.Qd2[i] : 0.0;
       else v += 2.0 * x.Q[i * n + j];
+      // upper triangle only: the update Vxx -= Qux' K reads (i, j) of the tiles r <= c and writes
+      // both (i, j) and its mirror, and nothing reads the lower triangle in between
       s.Vxx[i * BsCfg<n, m>::LDV + j] = v;
-      if (off) s.Vxx[j * BsCfg<n, m>::LDV + i] = v;
     }
   } else if (!VXX) {
     if (i < n) {                               // Qxu = Qux'                    (ilqr.py:656)
