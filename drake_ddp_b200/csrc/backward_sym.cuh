@@ -137,6 +137,25 @@ constexpr BsDeal bs_deal(int count, int base) {
   return d;
 }
 constexpr int bs_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+// the entries below `limit` of every warp's list, in the same order
+constexpr BsDeal bs_below(BsDeal in, int limit) {
+  BsDeal d = {};
+  for (int w = 0; w < 3; ++w)
+    for (int p = 0; p < in.cnt[w]; ++p)
+      if (in.list[w][p] < limit) d.list[w][d.cnt[w]++] = in.list[w][p];
+  return d;
+}
+// for every entry of `sub` its position in the same warp's list of `all`
+constexpr BsDeal bs_positions(BsDeal all, BsDeal sub) {
+  BsDeal d = {};
+  for (int w = 0; w < 3; ++w) {
+    d.cnt[w] = sub.cnt[w];
+    for (int q = 0; q < sub.cnt[w]; ++q)
+      for (int p = 0; p < all.cnt[w]; ++p)
+        if (all.list[w][p] == sub.list[w][q]) d.list[w][q] = p;
+  }
+  return d;
+}
 
 template <int n, int m>
 struct BsCfg {
@@ -172,7 +191,10 @@ struct BsCfg {
   // column strip c of K with its update tiles
   static constexpr BsDeal SD = bs_deal(TS, TN);
   static constexpr int MAXS = bs_max3(SD.cnt[0], SD.cnt[1], SD.cnt[2]);
-  static constexpr BsDeal KD = bs_deal(TN, TM);   // column strips of K (K_c and its update tiles)
+  // column strips of K (K_c and its update tiles): the warp's own Vxx strips, so that a tile
+  // Qxx(r, c) = lxx + M(r, c) never leaves the registers between the products and the update
+  static constexpr BsDeal KD = bs_below(SD, TN);
+  static constexpr BsDeal KP = bs_positions(SD, KD);   // where a K strip sits among the warp's stacked strips
   static constexpr int MAXK = bs_max3(KD.cnt[0], KD.cnt[1], KD.cnt[2]);
   // leading dimension of Vxx in shared memory: the A-operand fetch of the W product reads rows g,
   // columns 4 kk + tg; a half-warp (g = 0..3) is conflict-free when the row stride is 8 banks mod 32,
@@ -216,7 +238,6 @@ struct BsSmem {
   double Qu[m], g[m], Qd2[n];                 // Qd2 = diagonal of lxx = 2 Q
   alignas(8) uint64_t bar[2];                 // fx tile landed (per buffer)
   alignas(8) uint64_t barFu;
-  alignas(8) uint64_t barV;                   // every DMMA warp is done reading the old Vxx
   alignas(8) uint64_t barQ;                   // Qux complete and Quu^-1 ready
   alignas(8) uint64_t barS;                   // every DMMA warp is done reading fx / fu of the step
   int slot;                                   // CTA slot on this SM (deals the warp roles)
@@ -460,12 +481,12 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
   constexpr int TN = C::TN, TM = C::TM, KN = C::KN, KM = C::KM, TS = C::TS, TQ = C::TQ, NT = C::NT;
   constexpr int LDV = C::LDV;
   constexpr bool EVEN = C::EVEN;
-  constexpr BsDeal SD = C::SD, KD = C::KD;
+  constexpr BsDeal SD = C::SD, KD = C::KD, KP = C::KP;
   constexpr int NSTR = SD.cnt[W], NKST = KD.cnt[W];
   BsSmem<n, m>& s = *x.s;
   const Dev& d = x.d;
   const int g = x.g, tg = x.tg, T = d.T;
-  uint32_t parity[2] = {0, 0}, parityFu = 0, parityV = 0, parityQ = 0, parityS = 0;
+  uint32_t parity[2] = {0, 0}, parityFu = 0, parityQ = 0, parityS = 0;
   (void)parityS;
   int buf = 0;
   BS_PROF_DECL
@@ -541,14 +562,15 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
       bs_w_strips<n, m>(s, Fx, Fu, g, tg, SD.list[W][p0], SD.list[W][two ? p0 + 1 : p0], two);
     }
     __syncwarp();
-    if (!kBsNamed && x.lane == 0) mbar_arrive(&s.barV);   // this warp no longer reads the old Vxx
     BS_TICK(3);
 
     // ---- phase 2b: the other tiles M(r, c), r <= c, r < TQ, all strips of the warp in one sweep
-    // over S (an operand fragment of S feeds every strip that needs the row tile) ------------------
+    // over S (an operand fragment of S feeds every strip that needs the row tile).  The tiles stay
+    // in registers: their Qux / Quu elements are stored now, their Qxx elements become the
+    // accumulators of the Vxx update below ---------------------------------------------------------
+    constexpr int RMAX = (TQ < TS) ? TQ : TS;      // row tiles 0 .. RMAX-1 can be needed
+    double acc[C::MAXS][RMAX > 0 ? RMAX : 1][2];
     {
-      constexpr int RMAX = (TQ < TS) ? TQ : TS;      // row tiles 0 .. RMAX-1 can be needed
-      double acc[C::MAXS][RMAX > 0 ? RMAX : 1][2];
       const double* pw[C::MAXS];
 #pragma unroll
       for (int p0 = 0; p0 < C::MAXS; ++p0) {
@@ -585,33 +607,18 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
         if (C::TMA) named_bar_arrive(5, NT);
       } else if (x.lane == 0) mbar_arrive(&s.barS);
       BS_TICK(5);
-      // the first tile that lands in Vxx waits until every warp is done reading the old Vxx
-      if (kBsNamed) named_bar_sync(3, 32 * C::NMW);
-      else mbar_wait(&s.barV, parityV);
-      parityV ^= 1;
       BS_TICK(6);
 #pragma unroll
       for (int p0 = 0; p0 < NSTR; ++p0) {
         const int c = SD.list[W][p0];
+        if (c < TQ) continue;                      // strips below TQ hold Qxx elements only
 #pragma unroll
         for (int r = 0; r < RMAX; ++r)
           if (r <= c) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < 2; ++e)
               bs_route<n, m, false>(s, x, 8 * r + g, 8 * c + 2 * tg + e, acc[p0][r][e], r < c);
-              bs_route<n, m, true>(s, x, 8 * r + g, 8 * c + 2 * tg + e, acc[p0][r][e], r < c);
-            }
           }
-        // the Vxx part of the tiles computed early (only the tile that straddles n has one)
-        if (c >= TQ) {
-#pragma unroll
-          for (int q = 0; q < TS - TQ; ++q)
-            if (TQ + q <= c) {
-#pragma unroll
-              for (int e = 0; e < 2; ++e)
-                bs_route<n, m, true>(s, x, 8 * (TQ + q) + g, 8 * c + 2 * tg + e, hacc[p0][q][e], TQ + q < c);
-            }
-        }
       }
     }
     // ---- all Q-terms complete and Quu^-1 ready ---------------------------------------------------
@@ -669,12 +676,12 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
 #pragma unroll
       for (int p0 = 0; p0 < NKST; ++p0) {
         const int c = KD.list[W][p0];
-        double* kt = s.Wf + c * (n * 8);      // K strip, [m][8] (the W slices are dead by now)
+        double* kt = s.Wf + c * (n * 8);      // -K strip, [m][8] (the W slices are dead by now): the update subtracts
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
           const int r = 8 * i + g, col = 8 * c + 2 * tg;
           if (r < m) {
-            *reinterpret_cast<double2*>(kt + r * 8 + bs_wcol(r, 2 * tg)) = make_double2(kacc[p0][i][0], kacc[p0][i][1]);
+            *reinterpret_cast<double2*>(kt + r * 8 + bs_wcol(r, 2 * tg)) = make_double2(-kacc[p0][i][0], -kacc[p0][i][1]);
             if (EVEN) {
               if (col < n) *reinterpret_cast<double2*>(gK + r * n + col) = make_double2(kacc[p0][i][0], kacc[p0][i][1]);
             } else {
@@ -687,14 +694,34 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
     }
     __syncwarp();
     {
-      double acc[C::MAXK][TN][2];
+      // Vxx = Qxx - Qux' Quu^-1 Qux (ilqr.py:667), tiles r <= c of the warp's strips: the
+      // accumulators start from Qxx = lxx + M (ilqr.py:653; M is still in this warp's registers)
+      // and the products run against -K_c.  Every warp is past its W products here (barQ), so the
+      // old Vxx is dead; the mirror element is an exact copy.
+      double uacc[C::MAXK][TN][2];
       const double* pk[C::MAXK];
 #pragma unroll
       for (int p0 = 0; p0 < C::MAXK; ++p0) {
         const int c = KD.list[W][p0 < NKST ? p0 : 0];
+        const int sp = KP.list[W][p0 < NKST ? p0 : 0];   // the strip's place among the warp's stacked strips
         pk[p0] = s.Wf + c * (n * 8) + tg * 8 + bs_wcol(tg, g);
 #pragma unroll
-        for (int r = 0; r < TN; ++r) acc[p0][r][0] = acc[p0][r][1] = 0.0;
+        for (int r = 0; r < TN; ++r) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            double v = 0.0;
+            if (p0 < NKST && r <= c) {
+              v = (r < RMAX) ? acc[sp][r < RMAX ? r : 0][e] : hacc[sp][(r >= TQ && r - TQ < TS - TQ) ? r - TQ : 0][e];
+              const int i = 8 * r + g, j = 8 * c + 2 * tg + e;
+              if (x.diag) {
+                if (r == c) v += (i == j && i < n) ? s.Qd2[i] : 0.0;
+              } else if (i < n && j < n) {
+                v += 2.0 * x.Q[i * n + j];
+              }
+            }
+            uacc[p0][r][e] = v;
+          }
+        }
       }
 #pragma unroll
       for (int kk = 0; kk < KM; ++kk) {
@@ -711,7 +738,7 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
           const double a = kin ? s.Qux[(4 * kk + tg) * n + min(8 * r + g, n - 1)] : 0.0;
 #pragma unroll
           for (int p0 = 0; p0 < NKST; ++p0)
-            if (r <= KD.list[W][p0]) dmma(acc[p0][r], a, bk[p0]);
+            if (r <= KD.list[W][p0]) dmma(uacc[p0][r], a, bk[p0]);
         }
       }
 #pragma unroll
@@ -725,8 +752,8 @@ __device__ __forceinline__ void bs_dmma_warp(const BsCtx<n, m>& x) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int j = 8 * c + 2 * tg + e;
-            if (i < n && j < n) {                    // Vxx = Qxx - Qux' Quu^-1 Qux     (ilqr.py:667)
-              const double v = s.Vxx[i * LDV + j] - acc[p0][r][e];
+            if (i < n && j < n) {
+              const double v = uacc[p0][r][e];
               s.Vxx[i * LDV + j] = v;
               if (off) s.Vxx[j * LDV + i] = v;
             }
@@ -968,7 +995,6 @@ backward_sym_kernel(Dev d) {
     mbar_init(&s.bar[0], 1);
     mbar_init(&s.bar[1], 1);
     mbar_init(&s.barFu, 1);
-    mbar_init(&s.barV, NMW);
     mbar_init(&s.barQ, NMW + 1);
     mbar_init(&s.barS, NMW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
