@@ -12,11 +12,12 @@
 // where the lower block is needed.  The work is dealt by 8-wide COLUMN strips of S: the warp that
 // owns strip c computes W_c = Vxx S_c (all rows) into its private slice of shared memory and
 // then M(r, c) = S_r' W_c for r <= c from that slice alone -- no CTA barrier between the two
-// products, and with the strips dealt (5,0) (4,1) (3,2) the three warps carry 17 tiles each.  The
-// same holds for the gains: the warp that owns column strip c of K computes K_c = Quu^-1 Qux_c
-// and the tiles r <= c of the update Vxx -= Qux_r' K_c.  Per step that leaves two CTA barriers
-// (inputs ready / Q-terms ready) plus one split arrive-wait (every warp is done reading the old
-// Vxx before the first Qxx tile overwrites it).
+// products; the strips are dealt (5,0) (4,1) (3,2).  The same warp owns column strip c of the
+// gains and of the Vxx update: it computes K_c = Quu^-1 Qux_c and the tiles r <= c of
+// Vxx = Qxx - Qux_r' K_c, with its own tiles Qxx(r, c) = lxx + M(r, c) -- still in registers -- as
+// the accumulators of the products against -K_c.  Per step that leaves two CTA barriers (inputs
+// ready / Quu handed to the vector warp) and two mbarrier hand-offs (Q-terms and Quu^-1 complete /
+// fx, fu released); past the first nobody reads the old Vxx, so the update may overwrite it.
 //   DMMAs per step at (n, m) = (36, 12): 270 (W) + 189 (M) + 30 (K) + 45 (update) = 534, against
 //   681 for the unsymmetric schedule of round 1; the inverse adds 24 per Newton-Schulz pass.
 // The strips that hold fu columns go first, so Quu exists after a third of the products and the
@@ -399,21 +400,15 @@ __device__ __forceinline__ void bs_stacked(const double* Fx, const double* Fu, i
 }
 
 // ---- one DMMA warp: W is the warp's index (0..2), everything about its strips is static ----------
-// element routing of a stacked tile M(r, c): (i, j) stacked row / column, v the value.
-//   VXX = false: only the elements that go to Qux / Quu are stored; VXX = true: only those that go
-//   to Vxx (Qxx).  Splitting the two lets the Quu tiles leave before the old Vxx is released.
+// element routing of a stacked tile M(r, c): (i, j) stacked row / column, v the value: the
+// elements that belong to Qux / Quu are stored (VXX = false; the Qxx elements stay in the warp's
+// registers and become the accumulators of the Vxx update).
 template <int n, int m, bool VXX>
 __device__ __forceinline__ void bs_route(BsSmem<n, m>& s, const BsCtx<n, m>& x, int i, int j, double v, bool off) {
+  static_assert(!VXX, "Qxx tiles are no longer routed through shared memory");
   constexpr int NS = n + m;
   if (i >= NS || j >= NS) return;
-  if (i < n && j < n) {                        // Qxx = lxx + fx' Vxx fx        (ilqr.py:653)
-    if (VXX) {
-      if (x.diag) v += (i == j) ? s.Qd2[i] : 0.0;
-      else v += 2.0 * x.Q[i * n + j];
-      // upper triangle only: the update Vxx -= Qux' K reads (i, j) of the tiles r <= c and writes
-      // both (i, j) and its mirror, and nothing reads the lower triangle in between
-      s.Vxx[i * BsCfg<n, m>::LDV + j] = v;
-    }
+  if (i < n && j < n) {                        // Qxx = lxx + fx' Vxx fx        (ilqr.py:653): see the update
   } else if (!VXX) {
     if (i < n) {                               // Qxu = Qux'                    (ilqr.py:656)
       s.Qux[(j - n) * n + i] = v;
