@@ -168,10 +168,14 @@ def run_reference(args):
     if rank != 0:
         return
     prob = workload(args)
-    value, procs, dt, units = cpu_measure(args.horizon, args.steps, args.warmup, per_proc=1)
-    sample = (f"{procs} trajectories (one per process, OMP_NUM_THREADS=1) x {args.steps} iLQR iterations of the "
-              f"C4 problem after {args.warmup} warm-up iterations, same re-arm-on-convergence rule; oracle port = "
-              f"numpy restatement of ilqr.py + host build of the analytic model")
+    # 8 trajectories per process: the processes meet after every iteration, and with one trajectory
+    # each the slowest line search of the step sets the pace (measured: 449/s against 565/s); the
+    # same sample shape as the in-line cpu_baseline of the B200 arm
+    per_proc = 8
+    value, procs, dt, units = cpu_measure(args.horizon, args.steps, args.warmup, per_proc=per_proc)
+    sample = (f"{per_proc * procs} trajectories ({per_proc} per process, {procs} processes, OMP_NUM_THREADS=1) x "
+              f"{args.steps} iLQR iterations of the C4 problem after {args.warmup} warm-up iterations, same "
+              f"re-arm-on-convergence rule; oracle port = numpy restatement of ilqr.py + host build of the analytic model")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
