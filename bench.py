@@ -163,6 +163,42 @@ def cpu_measure(horizon, steps, warmup, per_proc=1):
     return units / dt, procs, dt, units
 
 
+def cpu_single_thread(horizon, iters=6):
+    """The reference's own execution model: ONE trajectory, one thread, phases timed
+    the way ilqr.py:364-372,696-699 times them (forward pass = line search + derivatives)."""
+    from drake_ddp_b200 import problems
+    from oracle.dynamics import HostDynamics
+    from oracle.ilqr_port import IlqrOracle
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=1)
+    except Exception:
+        limit = None
+    prob = problems.quadruped(horizon)
+    o = IlqrOracle(HostDynamics(prob.system), prob.N, delta=prob.delta, beta=prob.beta, gamma=prob.gamma)
+    o.set_initial_state(prob.batch_x0(1, seed=999)[0]); o.set_target_state(prob.x_nom)
+    o.set_running_cost(prob.Q, prob.R); o.set_terminal_cost(prob.Qf); o.set_initial_guess(prob.u_guess)
+    L = o.iterate(np.inf).L                       # warm-up iteration
+    ph = {"linesearch": 0.0, "derivs": 0.0, "backward": 0.0}
+    t_all = time.perf_counter()
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        eps, x, u, Lc, n_ls = o.linesearch(L)
+        t1 = time.perf_counter()
+        o.get_derivatives(x, u)
+        o.u_bar, o.x_bar = u, x
+        t2 = time.perf_counter()
+        o.backward_pass()
+        t3 = time.perf_counter()
+        ph["linesearch"] += t1 - t0; ph["derivs"] += t2 - t1; ph["backward"] += t3 - t2
+        L = float(Lc)
+    dt = time.perf_counter() - t_all
+    if limit is not None:
+        limit.restore_original_limits()
+    return {"value": iters / dt, "unit": UNIT, "cores": 1, "iterations": iters,
+            "phase_ms_per_iteration": {k: v / iters * 1e3 for k, v in ph.items()}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,7 +216,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args, prob, 1),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                             "single_thread": cpu_single_thread(args.horizon)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -567,7 +604,8 @@ def run_b200(args):
                 "value": cv, "unit": UNIT, "cores": procs, "kind": "port",
                 "sample": f"{cpu_per_proc * procs} trajectories ({cpu_per_proc} per process, {procs} processes, 1 thread each) x {cpu_steps} "
                           f"iLQR iterations of the same C4 problem after 1 warm-up iteration, same re-arm rule "
-                          f"({cunits} trajectory-iterations in {cdt:.1f} s wall)"}
+                          f"({cunits} trajectory-iterations in {cdt:.1f} s wall)",
+                "single_thread": cpu_single_thread(args.horizon)}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
