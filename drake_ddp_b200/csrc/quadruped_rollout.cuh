@@ -152,7 +152,11 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   auto stage = [&](int t, int buf) {   // SHARED: all threads of the warp
     char* dst = reinterpret_cast<char*>(stage_buf[buf]);
     const char* gK = reinterpret_cast<const char*>(d.K + ((size_t)b * d.T + t) * m * n);
-    for (int ch = wl; ch < 6 * n; ch += 32) cp_async16(dst + 16 * ch, gK + 16 * ch);
+#pragma unroll
+    for (int i = 0; i < (6 * n + 31) / 32; ++i) {   // unrolled: a loop branch per copy sits on the step's issue path
+      const int ch = wl + 32 * i;
+      if (ch < 6 * n) cp_async16(dst + 16 * ch, gK + 16 * ch);
+    }
     const char* gx = reinterpret_cast<const char*>(d.x_bar + ((size_t)b * d.N + t) * n);
     const char* gu = reinterpret_cast<const char*>(d.u_bar + ((size_t)b * d.T + t) * m);
     const char* gk = reinterpret_cast<const char*>(d.kappa + ((size_t)b * d.T + t) * m);
@@ -188,6 +192,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   // reciprocal mass / inertia of the base acceleration this lane computes (lanes 0..5), fetched once:
   // a ternary over global loads inside the step compiles to branches
   const double rcp_l = (lane < 3) ? p[20] : (lane == 3) ? p[21] : (lane == 4) ? p[22] : p[23];
+  const bool l_b0 = (lane & 1) != 0, l_b1 = (lane & 2) != 0, l_b2 = (lane & 4) != 0;
   double L = 0.0, E = 0.0;
   bool ok = true;
 #ifdef DDP_ROLL_PROFILE
@@ -285,7 +290,11 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
         }
       }
       L += sacc;
-      for (int r = lane; r < m; r += kRqLanes) uo[(size_t)t * m + r] = s.u[r];
+#pragma unroll
+      for (int k = 0; k < (m + kRqLanes - 1) / kRqLanes; ++k) {
+        const int r = lane + kRqLanes * k;
+        if (r < m) uo[(size_t)t * m + r] = s.u[r];
+      }
     }
     ROLL_TICK(3);
     const double ua = s.u[3 * leg], uh = s.u[3 * leg + 1], uk = s.u[3 * leg + 2];
@@ -356,7 +365,11 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       const double n4 = f[4] - (Ix - Iz) * vb[5] * vb[3];
       const double n5 = f[5] - (Iy - Ix) * vb[3] * vb[4];
       if (!QUAT) {   // Quadruped::base_acc: [linear | body angular]
-        const double num = (lane == 0) ? f[0] : (lane == 1) ? f[1] : (lane == 2) ? f[2] : (lane == 3) ? n3 : (lane == 4) ? n4 : n5;
+        // entry `lane` of (f0, f1, f2, n3, n4, n5) by a tree of selects on the lane's bits: the nested
+        // ternary over six values compiles to a branch ladder on the serial path of the substep
+        const double s01 = l_b0 ? f[1] : f[0], s23 = l_b0 ? n3 : f[2], s45 = l_b0 ? n5 : n4;
+        const double s03 = l_b1 ? s23 : s01;
+        const double num = l_b2 ? s45 : s03;
         double a = num * rcp_l;
         if (lane == 2) a -= grav;
         if (lane < 6) s.acc[lane] = a;
@@ -415,7 +428,8 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
           const double e1 = q1 + (0.5 * h) * (w0 * q0 + w1 * q3 - w2 * q2);
           const double e2 = q2 + (0.5 * h) * (w1 * q0 + w2 * q1 - w0 * q3);
           const double e3 = q3 + (0.5 * h) * (w2 * q0 + w0 * q2 - w1 * q1);
-          const double qe = (lane == 0) ? e0 : (lane == 1) ? e1 : (lane == 2) ? e2 : e3;
+          const double e01 = l_b0 ? e1 : e0, e23 = l_b0 ? e3 : e2;
+          const double qe = l_b1 ? e23 : e01;
           if (lane < 4) fin_step = fin_step && isfinite(qe);
           // position / joint entry that goes with velocity entry i >= 3: q index i + 1
 #pragma unroll
@@ -446,7 +460,11 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       continue;
     }
     E += ecoef * dv_t;                      //  (ilqr.py:326)
-    for (int j = lane; j < n; j += kRqLanes) xo[(size_t)(t + 1) * n + j] = s.x[j];
+#pragma unroll
+    for (int k = 0; k < (n + kRqLanes - 1) / kRqLanes; ++k) {
+      const int j = lane + kRqLanes * k;
+      if (j < n) xo[(size_t)(t + 1) * n + j] = s.x[j];
+    }
     ROLL_TICK(9);
   }
 #ifdef DDP_ROLL_PROFILE
