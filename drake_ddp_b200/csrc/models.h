@@ -141,12 +141,19 @@ typedef CartPoleT<true> CartPoleWall;
 
 // ------------------------------------------------------------------------------
 // Compliant sphere / rigid plane normal force, depth >= 0, saturating at R.
+// k23R = 2 / (3 R): a division is ~25 dependent instructions and sits on the serial path of a
+// contact step, so callers that evaluate the force every substep pass the quotient in (the
+// quadruped keeps it in its parameter vector, rounded once on the host: same value, same result).
 template <class S>
-DDP_HD S sphere_plane_force(const S& depth, double R, double E) {
+DDP_HD S sphere_plane_force(const S& depth, double R, double E, double k23R) {
   const double piE = 3.14159265358979323846 * E;
   if (val(depth) <= 0.0) return 0.0 * depth;
   if (val(depth) >= R) return S(piE * R * R / 3.0) + 0.0 * depth;
-  return piE * depth * depth * (1.0 - depth * (2.0 / (3.0 * R)));
+  return piE * depth * depth * (1.0 - depth * k23R);
+}
+template <class S>
+DDP_HD S sphere_plane_force(const S& depth, double R, double E) {
+  return sphere_plane_force(depth, R, E, 2.0 / (3.0 * R));
 }
 
 // ------------------------------------------------------------------------------
@@ -157,12 +164,12 @@ DDP_HD S sphere_plane_force(const S& depth, double R, double E) {
 //   v = [world linear velocity | body angular velocity | joint rates]        (18)
 // p = [dt, substeps, mass, Ixx, Iyy, Izz, Ij_abad, Ij_hip, Ij_knee, joint_damping,
 //      l_abad, l_thigh, l_shank, hip_x, hip_y, foot_radius, E, mu, v_stiction, g,
-//      1/mass, 1/Ixx, 1/Iyy, 1/Izz, 1/Ij_abad, 1/Ij_hip, 1/Ij_knee]
+//      1/mass, 1/Ixx, 1/Iyy, 1/Izz, 1/Ij_abad, 1/Ij_hip, 1/Ij_knee, 2/(3 foot_radius)]
 // The model divides by nothing but cos(pitch) and the slip speed: masses and inertias enter through
 // their reciprocals (p[20..26], rounded once on the host), because an fp64 division is ~25 dependent
 // instructions on the serial path of every rollout step.
 struct Quadruped {
-  static constexpr int n = 36, m = 12, np = 27;
+  static constexpr int n = 36, m = 12, np = 28;
   static constexpr int COOP = 4;  // step_coop: one leg per lane of a 4-lane group
 
   template <class S>
@@ -234,7 +241,7 @@ struct Quadruped {
       S bz = v[3] * ry - v[4] * rx + J20 * va + J21 * vh + J22 * vk;
       S wx = v[0] + B.R00 * bx + B.R01 * by + B.R02 * bz;
       S wy = v[1] + B.R10 * bx + B.R11 * by + B.R12 * bz;
-      S Fn = sphere_plane_force(depth, rf, E);
+      S Fn = sphere_plane_force(depth, rf, E, p[27]);
       S isl = 1.0 / sqrt_(wx * wx + wy * wy + vs * vs);
       S ftn = (mu * Fn) * isl;
       S ftx = -(ftn * wx);
@@ -414,7 +421,7 @@ struct Quadruped {
 // The rotation uses the normalised quaternion; the state itself is not renormalised.
 // Same parameter vector as Quadruped.
 struct QuadrupedQuat {
-  static constexpr int n = 37, m = 12, np = 27;
+  static constexpr int n = 37, m = 12, np = 28;
   static constexpr int COOP = 4;  // step_coop: one leg per lane of a 4-lane group
   template <class S>
   DDP_HD static void step(const S* x, const S* u, S* xn, const double* p) {

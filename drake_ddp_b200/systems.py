@@ -103,6 +103,7 @@ def quadruped(dt=4e-3, substeps=2, mass=8.252, inertia=(0.07, 0.26, 0.242),
     # masses and inertias enter the model through their reciprocals (csrc/models.h), rounded here once
     p += [1.0 / mass, *(1.0 / np.asarray(inertia, dtype=np.float64)),
           *(1.0 / np.asarray(joint_inertia, dtype=np.float64))]
+    p += [2.0 / (3.0 * foot_radius)]      # the contact law's 2/(3R), same reason
     return AnalyticSystem("quadruped", MODEL_QUADRUPED, 36, 12, np.array(p, dtype=np.float64))
 
 
