@@ -161,5 +161,18 @@ DDP_HD Dual<K> sqrt_(const Dual<K>& a) {
   for (int k = 0; k < K; ++k) r.d[k] = h * a.d[k];
   return r;
 }
+// 1 / sqrt(a).  Plain double on the device: ONE rsqrt (max error 1 ulp) instead of a square root
+// followed by a division, both of which sit on the serial path of a contact step (the same class of
+// host / device difference as sincos: the host keeps 1 / sqrt).  The dual version keeps the
+// arithmetic of 1.0 / sqrt_(a), so the Jacobians are what they were.
+DDP_HD double inv_sqrt_(double a) {
+#if defined(__CUDA_ARCH__)
+  return ::rsqrt(a);
+#else
+  return 1.0 / ::sqrt(a);
+#endif
+}
+template <int K>
+DDP_HD Dual<K> inv_sqrt_(const Dual<K>& a) { return 1.0 / sqrt_(a); }
 
 }  // namespace ddp

@@ -242,7 +242,7 @@ struct Quadruped {
       S wx = v[0] + B.R00 * bx + B.R01 * by + B.R02 * bz;
       S wy = v[1] + B.R10 * bx + B.R11 * by + B.R12 * bz;
       S Fn = sphere_plane_force(depth, rf, E, p[27]);
-      S isl = 1.0 / sqrt_(wx * wx + wy * wy + vs * vs);
+      S isl = inv_sqrt_(wx * wx + wy * wy + vs * vs);
       S ftn = (mu * Fn) * isl;
       S ftx = -(ftn * wx);
       S fty = -(ftn * wy);
@@ -445,7 +445,7 @@ struct QuadrupedQuat {
     }
     for (int it = 0; it < sub; ++it) {
       // rotation matrix of the normalised quaternion (body -> world)
-      S inn = 1.0 / sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+      S inn = inv_sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
       S a = qt[0] * inn, b = qt[1] * inn, c = qt[2] * inn, d = qt[3] * inn;
       Qd::BasePose<S> B;
       B.R00 = 1.0 - 2.0 * (c * c + d * d); B.R01 = 2.0 * (b * c - a * d); B.R02 = 2.0 * (b * d + a * c);
@@ -542,7 +542,7 @@ struct QuadrupedQuat {
     const double uk = Qd::pick4(lane, u[2], u[5], u[8], u[11]);
     const double sx = (lane < 2) ? 1.0 : -1.0, sd = (lane & 1) ? 1.0 : -1.0;
     for (int it = 0; it < sub; ++it) {
-      double inn = 1.0 / sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
+      double inn = inv_sqrt_(qt[0] * qt[0] + qt[1] * qt[1] + qt[2] * qt[2] + qt[3] * qt[3]);
       double a = qt[0] * inn, b = qt[1] * inn, c = qt[2] * inn, d = qt[3] * inn;
       Qd::BasePose<double> B;
       B.R00 = 1.0 - 2.0 * (c * c + d * d); B.R01 = 2.0 * (b * c - a * d); B.R02 = 2.0 * (b * d + a * c);

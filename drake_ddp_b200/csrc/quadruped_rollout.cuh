@@ -327,7 +327,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       } else {
         // rotation matrix of the normalised quaternion (QuadrupedQuat::step), every lane
         const double q0 = s.x[0], q1 = s.x[1], q2 = s.x[2], q3 = s.x[3];
-        const double inn = 1.0 / sqrt_(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        const double inn = inv_sqrt_(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
         const double a = q0 * inn, b_ = q1 * inn, c_ = q2 * inn, d_ = q3 * inn;
         B.R00 = 1.0 - 2.0 * (c_ * c_ + d_ * d_); B.R01 = 2.0 * (b_ * c_ - a * d_); B.R02 = 2.0 * (b_ * d_ + a * c_);
         B.R10 = 2.0 * (b_ * c_ + a * d_); B.R11 = 1.0 - 2.0 * (b_ * b_ + d_ * d_); B.R12 = 2.0 * (c_ * d_ - a * b_);
