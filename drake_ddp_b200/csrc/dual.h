@@ -163,8 +163,9 @@ DDP_HD Dual<K> sqrt_(const Dual<K>& a) {
 }
 // 1 / sqrt(a).  Plain double on the device: ONE rsqrt (max error 1 ulp) instead of a square root
 // followed by a division, both of which sit on the serial path of a contact step (the same class of
-// host / device difference as sincos: the host keeps 1 / sqrt).  The dual version keeps the
-// arithmetic of 1.0 / sqrt_(a), so the Jacobians are what they were.
+// host / device difference as sincos: the host keeps 1 / sqrt).  The dual version reproduces
+// 1.0 / sqrt_(a) bit for bit with one division less: sqrt_ divides 0.5 by the root and the quotient
+// divides 1 by it again, and 0.5 / r == 0.5 * (1 / r) exactly (a power of two commutes with rounding).
 DDP_HD double inv_sqrt_(double a) {
 #if defined(__CUDA_ARCH__)
   return ::rsqrt(a);
@@ -173,6 +174,15 @@ DDP_HD double inv_sqrt_(double a) {
 #endif
 }
 template <int K>
-DDP_HD Dual<K> inv_sqrt_(const Dual<K>& a) { return 1.0 / sqrt_(a); }
+DDP_HD Dual<K> inv_sqrt_(const Dual<K>& a) {
+  Dual<K> r;
+  const double ib = 1.0 / ::sqrt(a.v);
+  const double h = 0.5 * ib;          // sqrt_: d sqrt = (0.5 / sqrt) da
+  const double s = -ib * ib;          // 1 / b: d = -(1 / b^2) db
+  r.v = ib;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = s * (h * a.d[k]);
+  return r;
+}
 
 }  // namespace ddp
