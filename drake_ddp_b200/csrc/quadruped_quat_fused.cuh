@@ -24,6 +24,17 @@
 
 namespace ddp {
 
+// entry i (0..3 / 0..2) of a few values that live in registers, as a tree of selects on the bits
+// of i: a nested ternary over more than two values compiles to a branch ladder (and these sit on
+// the serial path of a point)
+__device__ __forceinline__ double qq_sel4(int i, double a, double b, double c, double d) {
+  const bool b0 = (i & 1) != 0, b1 = (i & 2) != 0;
+  const double lo = b0 ? b : a, hi = b0 ? d : c;
+  return b1 ? hi : lo;
+}
+__device__ __forceinline__ double qq_sel3(int i, double a, double b, double c) { return qq_sel4(i, a, b, c, c); }
+
+
 struct QqWarpSmem {
   double J1[40 * kQfLd];    // Jacobian of substep 1, rows = entries of x1 (37; rows 37..39 stay zero), cols = [x0 (37) | u (12)]
   double Z[20 * kQfLd];     // d(body-frame v+) / d zeta of the current substep; substep 2: transformed in place to J2's velocity rows
@@ -248,11 +259,11 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         const int jl = (lane >= 6 && lane < 18) ? (lane - 6) / 3 : 0, jk = (lane >= 6 && lane < 18) ? (lane - 6) % 3 : 0;
         const double a0 = __shfl_sync(full, av[0], 8 * jl), a1 = __shfl_sync(full, av[1], 8 * jl),
                      a2 = __shfl_sync(full, av[2], 8 * jl);
-        const double aj = (jk == 0) ? a0 : ((jk == 1) ? a1 : a2);
+        const double aj = qq_sel3(jk, a0, a1, a2);
         double vnew;   // velocity entry `lane` of [omega (3) | v_lin (3) | joint rates (12)]
-        if (lane < 3) vnew = (lane == 0) ? wn0 : (lane == 1) ? wn1 : wn2;
+        if (lane < 3) vnew = qq_sel3(lane, wn0, wn1, wn2);
         else if (lane < 6) {
-          double a = ((lane == 3) ? f[0] : (lane == 4) ? f[1] : f[2]) * p[20];
+          double a = qq_sel3(lane - 3, f[0], f[1], f[2]) * p[20];
           if (lane == 5) a -= grav;
           vnew = xin[19 + lane] + h * a;
         } else vnew = xin[19 + (lane < 18 ? lane : 0)] + h * aj;
@@ -264,13 +275,13 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
           xout[19 + lane] = vnew;
           if (lane >= 3) xout[lane + 1] = xin[lane + 1] + h * vnew;   // position / joint entry of velocity entry `lane`
         }
-        if (lane < 4) xout[lane] = (lane == 0) ? e0 : (lane == 1) ? e1 : (lane == 2) ? e2 : e3;
+        if (lane < 4) xout[lane] = qq_sel4(lane, e0, e1, e2, e3);
       }
       __syncwarp();
       // gyroscopic terms of the body angular rows (d/d omega_body of the omega x I omega term): entry
       // (gy_off) += gy_coef * omega_body[gy_w], constants per lane (branch-free)
       {
-        const double wsel = (gy_w == 0) ? vloc[3] : ((gy_w == 1) ? vloc[4] : vloc[5]);
+        const double wsel = qq_sel3(gy_w, vloc[3], vloc[4], vloc[5]);
         if (lane < 6) Z[gy_off] += gy_coef * wsel;
       }
       __syncwarp();
@@ -306,7 +317,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         if (c < 4) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const double gk = (c == 0) ? G[k][0] : (c == 1) ? G[k][1] : (c == 2) ? G[k][2] : G[k][3];
+            const double gk = qq_sel4(c, G[k][0], G[k][1], G[k][2], G[k][3]);
             ck[q][k] = gk;
           }
 #pragma unroll
@@ -316,7 +327,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
         } else if (c >= 19 && c < 22) {
           const int i = c - 19;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) dk[q][j] = (i == 0) ? R[0][j] : (i == 1) ? R[1][j] : R[2][j];
+          for (int j = 0; j < 3; ++j) dk[q][j] = qq_sel3(i, R[0][j], R[1][j], R[2][j]);
 #pragma unroll
           for (int r = 0; r < 3; ++r) wx[q][r] = (r == i) ? 1.0 : 0.0;
         } else if (c == 6) {
@@ -365,7 +376,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
           for (int a = 0; a < 4; ++a) {
             double v = hq * (Bq[a][0] * vr[0][q] + Bq[a][1] * vr[1][q] + Bq[a][2] * vr[2][q]);
             if (c < 4) {
-              const double ac = (c == 0) ? A[a][0] : (c == 1) ? A[a][1] : (c == 2) ? A[a][2] : A[a][3];
+              const double ac = qq_sel4(c, A[a][0], A[a][1], A[a][2], A[a][3]);
               v += ((a == c) ? 1.0 : 0.0) + hq * ac;
             }
             s.J1[a * LD + c] = v;
