@@ -185,4 +185,35 @@ DDP_HD Dual<K> inv_sqrt_(const Dual<K>& a) {
   return r;
 }
 
+// r = sqrt(q) when 1 / r is wanted too (a unit normal, a friction direction), and x / r through
+// it.  Plain double on the device: one rsqrt, r = q * (1 / r), x / r = x * (1 / r), instead of a
+// square root and a division per use on the serial path of a contact step.  The host and the dual
+// path keep sqrt and x / r: their arithmetic (oracle, golden vectors, Jacobians) is what it was.
+DDP_HD double sqrt_pair_(double q, double* inv) {
+#if defined(__CUDA_ARCH__)
+  const double i = ::rsqrt(q);
+  *inv = i;
+  return q * i;
+#else
+  *inv = 0.0;
+  return ::sqrt(q);
+#endif
+}
+DDP_HD double div_root_(double x, double root, double inv) {
+#if defined(__CUDA_ARCH__)
+  (void)root;
+  return x * inv;
+#else
+  (void)inv;
+  return x / root;
+#endif
+}
+template <int K>
+DDP_HD Dual<K> sqrt_pair_(const Dual<K>& q, Dual<K>* inv) {
+  *inv = q;   // not used by the dual path
+  return sqrt_(q);
+}
+template <int K>
+DDP_HD Dual<K> div_root_(const Dual<K>& x, const Dual<K>& root, const Dual<K>&) { return x / root; }
+
 }  // namespace ddp

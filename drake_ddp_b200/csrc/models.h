@@ -672,32 +672,36 @@ struct ArmBall {
                               Loads<S>& o) {
     const double rt = p[11], rb = p[12], mb = p[13], E = p[14], mu = p[15], vs = p[16];
     const double g = p[17], diss = p[19];
+    // functions of the parameters alone, outside the contact branches so that they leave the substep loop
+    const double Re = rt * rb / (rt + rb);
+    const double k23Re = 2.0 / (3.0 * Re), k23rb = 2.0 / (3.0 * rb);
     S fbx = 0.0 * px, fby = fbx, fbz = fbx - mb * g;  // force on ball
     S tbx = 0.0 * px, tby = tbx, tbz = tbx;           // torque on ball (world)
     S ftx = 0.0 * px, fty = ftx, ftz = ftx;           // force on tool tip
     // tip sphere vs ball
     {
       S nx = bx_ - px, ny = by_ - py, nz = bz_ - pz;
-      S dist = sqrt_(nx * nx + ny * ny + nz * nz + 1e-12);
+      S idist;
+      S dist = sqrt_pair_(nx * nx + ny * ny + nz * nz + 1e-12, &idist);
       S depth = (rt + rb) - dist;
       if (val(depth) > 0.0) {
-        nx = nx / dist; ny = ny / dist; nz = nz / dist;  // tip -> ball
-        const double Re = rt * rb / (rt + rb);
+        nx = div_root_(nx, dist, idist); ny = div_root_(ny, dist, idist); nz = div_root_(nz, dist, idist);  // tip -> ball
         // relative velocity of ball surface point w.r.t. tip at the contact
         S cxr = -(rb)*nx, cyr = -(rb)*ny, czr = -(rb)*nz;  // contact point rel. ball centre
         S rvx = bv[0] + (w[1] * czr - w[2] * cyr) - tvx;
         S rvy = bv[1] + (w[2] * cxr - w[0] * czr) - tvy;
         S rvz = bv[2] + (w[0] * cyr - w[1] * cxr) - tvz;
         S vn = rvx * nx + rvy * ny + rvz * nz;   // separation rate = -depth rate
-        S Fn = sphere_plane_force(depth, Re, E);
+        S Fn = sphere_plane_force(depth, Re, E, k23Re);
         S hc = 1.0 - diss * vn;
         if (val(hc) < 0.0) hc = S(0.0);
         Fn = Fn * hc;
         S tx = rvx - vn * nx, ty = rvy - vn * ny, tz = rvz - vn * nz;
-        S sl = sqrt_(tx * tx + ty * ty + tz * tz + vs * vs);
-        S cfx = Fn * nx - (mu * Fn) * tx / sl;
-        S cfy = Fn * ny - (mu * Fn) * ty / sl;
-        S cfz = Fn * nz - (mu * Fn) * tz / sl;
+        S isl;
+        S sl = sqrt_pair_(tx * tx + ty * ty + tz * tz + vs * vs, &isl);
+        S cfx = Fn * nx - div_root_((mu * Fn) * tx, sl, isl);
+        S cfy = Fn * ny - div_root_((mu * Fn) * ty, sl, isl);
+        S cfz = Fn * nz - div_root_((mu * Fn) * tz, sl, isl);
         fbx = fbx + cfx; fby = fby + cfy; fbz = fbz + cfz;
         tbx = tbx + (cyr * cfz - czr * cfy);
         tby = tby + (czr * cfx - cxr * cfz);
@@ -709,15 +713,16 @@ struct ArmBall {
     {
       S depth = rb - bz_;
       if (val(depth) > 0.0) {
-        S Fn = sphere_plane_force(depth, rb, E);
+        S Fn = sphere_plane_force(depth, rb, E, k23rb);
         S hc = 1.0 - diss * bv[2];
         if (val(hc) < 0.0) hc = S(0.0);
         Fn = Fn * hc;
         // contact point velocity: v + w x (0,0,-rb)
         S cvx = bv[0] - w[1] * rb;
         S cvy = bv[1] + w[0] * rb;
-        S sl = sqrt_(cvx * cvx + cvy * cvy + vs * vs);
-        S fx_ = -(mu * Fn) * cvx / sl, fy_ = -(mu * Fn) * cvy / sl;
+        S isl;
+        S sl = sqrt_pair_(cvx * cvx + cvy * cvy + vs * vs, &isl);
+        S fx_ = div_root_(-(mu * Fn) * cvx, sl, isl), fy_ = div_root_(-(mu * Fn) * cvy, sl, isl);
         fbx = fbx + fx_; fby = fby + fy_; fbz = fbz + Fn;
         // torque = (0,0,-rb) x (fx, fy, Fn)
         tbx = tbx + rb * fy_;
