@@ -163,9 +163,10 @@ DDP_HD Dual<K> sqrt_(const Dual<K>& a) {
 }
 // 1 / sqrt(a).  Plain double on the device: ONE rsqrt (max error 1 ulp) instead of a square root
 // followed by a division, both of which sit on the serial path of a contact step (the same class of
-// host / device difference as sincos: the host keeps 1 / sqrt).  The dual version reproduces
-// 1.0 / sqrt_(a) bit for bit with one division less: sqrt_ divides 0.5 by the root and the quotient
-// divides 1 by it again, and 0.5 / r == 0.5 * (1 / r) exactly (a power of two commutes with rounding).
+// host / device difference as sincos: the host keeps 1 / sqrt).  The dual version takes its value
+// from the same function and forms the derivative of 1.0 / sqrt_(a) with one division less: sqrt_
+// divides 0.5 by the root and the quotient divides 1 by it again, and 0.5 / r == 0.5 * (1 / r)
+// exactly (a power of two commutes with rounding), so on the host it is 1.0 / sqrt_(a) bit for bit.
 DDP_HD double inv_sqrt_(double a) {
 #if defined(__CUDA_ARCH__)
   return ::rsqrt(a);
@@ -176,7 +177,7 @@ DDP_HD double inv_sqrt_(double a) {
 template <int K>
 DDP_HD Dual<K> inv_sqrt_(const Dual<K>& a) {
   Dual<K> r;
-  const double ib = 1.0 / ::sqrt(a.v);
+  const double ib = inv_sqrt_(a.v);   // device: rsqrt, like the plain-double path
   const double h = 0.5 * ib;          // sqrt_: d sqrt = (0.5 / sqrt) da
   const double s = -ib * ib;          // 1 / b: d = -(1 / b^2) db
   r.v = ib;
@@ -187,8 +188,9 @@ DDP_HD Dual<K> inv_sqrt_(const Dual<K>& a) {
 
 // r = sqrt(q) when 1 / r is wanted too (a unit normal, a friction direction), and x / r through
 // it.  Plain double on the device: one rsqrt, r = q * (1 / r), x / r = x * (1 / r), instead of a
-// square root and a division per use on the serial path of a contact step.  The host and the dual
-// path keep sqrt and x / r: their arithmetic (oracle, golden vectors, Jacobians) is what it was.
+// square root and a division per use on the serial path of a contact step (plain double and dual
+// alike).  The host keeps sqrt and x / r: the arithmetic of the oracle and of the golden vectors is
+// what it was.
 DDP_HD double sqrt_pair_(double q, double* inv) {
 #if defined(__CUDA_ARCH__)
   const double i = ::rsqrt(q);
@@ -210,10 +212,23 @@ DDP_HD double div_root_(double x, double root, double inv) {
 }
 template <int K>
 DDP_HD Dual<K> sqrt_pair_(const Dual<K>& q, Dual<K>* inv) {
-  *inv = q;   // not used by the dual path
+#if defined(__CUDA_ARCH__)
+  *inv = inv_sqrt_(q);
+  return q * (*inv);
+#else
+  *inv = q;   // not used on the host
   return sqrt_(q);
+#endif
 }
 template <int K>
-DDP_HD Dual<K> div_root_(const Dual<K>& x, const Dual<K>& root, const Dual<K>&) { return x / root; }
+DDP_HD Dual<K> div_root_(const Dual<K>& x, const Dual<K>& root, const Dual<K>& inv) {
+#if defined(__CUDA_ARCH__)
+  (void)root;
+  return x * inv;
+#else
+  (void)inv;
+  return x / root;
+#endif
+}
 
 }  // namespace ddp
