@@ -143,7 +143,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
       double* Z = s.Z;
       // ---- base: rotation of the normalised quaternion, body-frame twist -----------------------
       const double q0 = xin[0], q1 = xin[1], q2 = xin[2], q3 = xin[3];
-      const double inn = 1.0 / sqrt_(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+      const double inn = inv_sqrt_(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
       const double qa = q0 * inn, qb = q1 * inn, qc = q2 * inn, qd = q3 * inn;
       double R[3][3];
       R[0][0] = 1.0 - 2.0 * (qc * qc + qd * qd); R[0][1] = 2.0 * (qb * qc - qa * qd); R[0][2] = 2.0 * (qb * qd + qa * qc);
