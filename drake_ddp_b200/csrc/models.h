@@ -620,9 +620,10 @@ struct QuadrupedQuat {
 // compliant table (sphere/plane contact) with regularised friction at both contacts.
 // Normal forces carry Hunt-Crossley dissipation: Fn = Fe(depth) * max(0, 1 + d * depth_rate).
 // p = [dt, substeps, Ij, joint_damping, d0..d6 (7), tip_radius, ball_radius, ball_mass,
-//      E, mu, v_stiction, g, base_z, dissipation]
+//      E, mu, v_stiction, g, base_z, dissipation,
+//      Re = rt rb / (rt + rb), 2 / (3 Re), 2 / (3 rb)]
 struct ArmBall {
-  static constexpr int n = 27, m = 7, np = 20;
+  static constexpr int n = 27, m = 7, np = 23;
   static constexpr int COOP = 1;
 
   // tool frame while walking up the chain: rotation (rows x, y, z of the world axes) and origin
@@ -672,9 +673,9 @@ struct ArmBall {
                               Loads<S>& o) {
     const double rt = p[11], rb = p[12], mb = p[13], E = p[14], mu = p[15], vs = p[16];
     const double g = p[17], diss = p[19];
-    // functions of the parameters alone, outside the contact branches so that they leave the substep loop
-    const double Re = rt * rb / (rt + rb);
-    const double k23Re = 2.0 / (3.0 * Re), k23rb = 2.0 / (3.0 * rb);
+    // functions of the parameters alone, rounded once on the host (systems.arm_ball): three divisions
+    // per substep otherwise (the compiler cannot move loads of p[] out of a loop that stores)
+    const double Re = p[20], k23Re = p[21], k23rb = p[22];   // rt rb / (rt + rb), 2 / (3 Re), 2 / (3 rb)
     S fbx = 0.0 * px, fby = fbx, fbz = fbx - mb * g;  // force on ball
     S tbx = 0.0 * px, tby = tbx, tbz = tbx;           // torque on ball (world)
     S ftx = 0.0 * px, fty = ftx, ftz = ftx;           // force on tool tip

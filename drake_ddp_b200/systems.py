@@ -123,6 +123,9 @@ def arm_ball(dt=1e-2, substeps=4, joint_inertia=0.3, joint_damping=0.5,
     than the script's 5e6 so the explicit contact stays well inside its stability limit."""
     p = [dt, float(substeps), joint_inertia, joint_damping, *links, tip_radius, ball_radius,
          ball_mass, modulus, mu, v_stiction, g, base_z, dissipation]
+    # parameter-only quotients of the contact laws (csrc/models.h ArmBall::contacts), rounded here once
+    r_eff = tip_radius * ball_radius / (tip_radius + ball_radius)
+    p += [r_eff, 2.0 / (3.0 * r_eff), 2.0 / (3.0 * ball_radius)]
     return AnalyticSystem("arm_ball", MODEL_ARM_BALL, 27, 7, np.array(p, dtype=np.float64))
 
 
