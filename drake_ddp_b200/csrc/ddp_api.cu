@@ -540,6 +540,7 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
     s->quad_fused = !(mode && std::string(mode) == "ad");
   }
   d.params = params;
+  for (int i = 0; i < 32; ++i) d.pm[i] = (i < np) ? params_host[i] : 0.0;
   GUARD(s);
   // from here on a failure must release what was acquired: run the rest in a lambda and
   // destroy the half-built solver if it reports an error

@@ -23,6 +23,11 @@ struct Dev {
   const double *u_min, *u_max;
   double* u_lim_buf;
   const double* params;
+  // the first kParamsInline model parameters by value: a kernel argument lives in the constant
+  // bank, so p[k] with a literal k becomes an instruction operand (no load, no register, nothing
+  // for the compiler to keep inside a loop that stores); the hand-written quadruped / arm kernels
+  // read their parameters from here (models with more parameters use `params` only)
+  double pm[32];
   const double *Q, *R, *Qf, *x_nom, *x0, *eps_table;
   double *x_bar, *u_bar, *K, *kappa, *dV, *fx, *fu;
   double *xc, *uc, *Lc, *Ec;
@@ -46,6 +51,13 @@ struct Dev {
   unsigned char *flag, *done;
   int *segs[2], *nseg[2], *evallist, *evalcount;
 };
+
+// Parameters of a model: from the kernel argument (constant bank) when they fit Dev::pm
+template <class Model>
+__device__ __forceinline__ const double* model_params(const Dev& d) {
+  if constexpr (Model::np <= 32) return d.pm;
+  else return d.params;
+}
 
 // Thread mapping per model size class.
 template <class Model>
@@ -207,8 +219,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(Dev d, int ls_base, int pe
       else u[r] = __shfl_sync(mask, mine[r / G], gbase + (r % G));
     }
     // x_{t+1} = f(x_t, u_t)                                          (ilqr.py:316)
-    if constexpr (Model::COOP == G && G > 1) Model::step_coop(lane, mask, gbase, x, u, xn, d.params);
-    else Model::template step<double>(x, u, xn, d.params);
+    if constexpr (Model::COOP == G && G > 1) Model::step_coop(lane, mask, gbase, x, u, xn, model_params<Model>(d));
+    else Model::template step<double>(x, u, xn, model_params<Model>(d));
     bool fin = true;
 #pragma unroll
     for (int j = 0; j < n; ++j) fin = fin && isfinite(xn[j]);
@@ -687,7 +699,7 @@ __global__ void __launch_bounds__(128, (Model::n > 8 ? DDP_LIN_MINB : 1)) linear
 #pragma unroll
       for (int k = 0; k < K; ++k) us[j].d[k] = ((pass * K + k) * G + lane == n + j) ? 1.0 : 0.0;
     }
-    Model::template step<D>(xs, us, out, d.params);
+    Model::template step<D>(xs, us, out, model_params<Model>(d));
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int g = (pass * K + k) * G + lane;

@@ -70,7 +70,7 @@ quad_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   QfWarpSmem& s = reinterpret_cast<QfWarpSmem*>(qf_raw)[warp];
   const unsigned full = 0xffffffffu;
-  const double* p = d.params;
+  const double* p = d.pm;   // constant bank (Dev::pm)
   const double h = p[0] / 2.0;
   const double Ix = p[3], Iy = p[4], Iz = p[5];
   const int T = d.T;

@@ -55,7 +55,7 @@ quad_quat_fused_kernel(Dev d, const int* list, const int* count, int n_items) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   QqWarpSmem& s = reinterpret_cast<QqWarpSmem*>(qq_raw)[warp];
   const unsigned full = 0xffffffffu;
-  const double* p = d.params;
+  const double* p = d.pm;   // constant bank (Dev::pm)
   const double h = p[0] / 2.0;
   const double Ix = p[3], Iy = p[4], Iz = p[5], grav = p[19];
   const int T = d.T;

@@ -126,7 +126,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   const int wl = threadIdx.x & 31, gbase = wl & ~7;
   const unsigned mask = 0xFFu << gbase;
   RqCandSmem& s = sm[cand];
-  const double* p = d.params;
+  const double* p = d.pm;   // constant bank (Dev::pm)
   const int sub_n = (int)p[1];
   const double h = p[0] / sub_n;
   const double eps = d.eps_table[min(c, d.n_eps - 1)];
