@@ -33,7 +33,11 @@ struct alignas(16) RaCandSmem {
   double sc[14];       // sin, cos of the seven joint angles of the substep
 };
 
-__global__ void __launch_bounds__(kRaLanes * kRaCands, 4)
+// MINB: resident CTAs per SM the register budget is sized for.  A launch of at most 2 CTAs per SM
+// (C5: 512 trajectories x 8 candidates = 256 CTAs) takes the 2-CTA build: 255 registers, nothing
+// spilled on the serial path; larger launches keep 4 CTAs per SM so that they stay one wave.
+template <int MINB>
+__global__ void __launch_bounds__(kRaLanes * kRaCands, MINB)
 rollout_arm8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   typedef ArmBall Ab;
   constexpr int n = 27, m = 7;

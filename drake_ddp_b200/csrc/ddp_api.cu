@@ -51,6 +51,7 @@ struct ddp_solver {
   bool quad_fused;       // fused structured quadruped linearization (DDP_QUAD_LINEARIZE=fused|ad)
   bool arm_rollout8;     // 8-lane arm + ball rollout (DDP_ARM_ROLLOUT=generic selects rollout_kernel)
   int quad_sub;          // substeps of the quadruped model (the fused linearization needs 2)
+  int sms;               // SMs of the solver's device (0: not queried yet)
   // array table
   double* darr[16];
   size_t dsize[16];
@@ -151,6 +152,11 @@ int model_dims(int model_id, int* n, int* m, int* np) {
 
 inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
+int device_sms(ddp_solver* s) {
+  if (!s->sms) cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, s->device);
+  return s->sms > 0 ? s->sms : 1;
+}
+
 // ---- templated launchers ---------------------------------------------------------------
 template <class Model>
 int launch_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
@@ -235,7 +241,11 @@ int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {
     return 0;
   }
   if (s->arm_rollout8 && s->model == MODEL_ARM_BALL && s->d.diag_cost) {
-    rollout_arm8_kernel<<<cdiv(n_items, kRaCands), kRaLanes * kRaCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+    const int ctas = cdiv(n_items, kRaCands);
+    if (ctas <= 2 * device_sms(s))
+      rollout_arm8_kernel<2><<<ctas, kRaLanes * kRaCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+    else
+      rollout_arm8_kernel<4><<<ctas, kRaLanes * kRaCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
     s->launches++;
     return 0;
   }
@@ -511,6 +521,7 @@ int ddp_create(ddp_solver_t** out, int model_id, const double* params_host, int 
   s->timings_valid = false;
   s->cfg_bwd = s->cfg_bwd_sym = false;
   s->fused_ctas = 0;
+  s->sms = 0;
   s->h_counters = nullptr;
   for (int i = 0; i < 4; ++i) s->ev[i] = nullptr;
   s->scalar_backward = getenv("DDP_SCALAR_BACKWARD") != nullptr;
