@@ -224,11 +224,17 @@ int launch_backward(ddp_solver* s) {
 
 template <bool QUAT>
 void launch_rollout_quad8(ddp_solver* s, int ls_base, int per_traj, int n_items) {
-  if (ls_base == 0 && per_traj == kRqCands && n_items == s->d.B * kRqCands)
-    rollout_quad8_kernel<true, QUAT><<<s->d.B, kRqLanes * kRqCands, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
-  else
-    rollout_quad8_kernel<false, QUAT><<<cdiv(n_items, kRqCands), kRqLanes * kRqCands, 0, s->stream>>>(
-        s->d, ls_base, per_traj, n_items);
+  const bool shared = ls_base == 0 && per_traj == kRqCands && n_items == s->d.B * kRqCands;
+  const int ctas = shared ? s->d.B : cdiv(n_items, kRqCands);
+  const bool few = ctas <= 4 * device_sms(s);   // the high-register build: four CTAs (8 warps x 255 registers) per SM
+  const int nt = kRqLanes * kRqCands;
+  if (shared) {
+    if (few) rollout_quad8_kernel<true, QUAT, 3><<<ctas, nt, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+    else rollout_quad8_kernel<true, QUAT, 7><<<ctas, nt, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+  } else {
+    if (few) rollout_quad8_kernel<false, QUAT, 3><<<ctas, nt, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+    else rollout_quad8_kernel<false, QUAT, 7><<<ctas, nt, 0, s->stream>>>(s->d, ls_base, per_traj, n_items);
+  }
   s->launches++;
 }
 int do_rollout(ddp_solver* s, int ls_base, int per_traj, int n_items) {

@@ -82,8 +82,12 @@ __device__ long long g_roll_prof[16];
 #define ROLL_TICK(i)
 #endif
 
-template <bool SHARED, bool QUAT>
-__global__ void __launch_bounds__(kRqLanes * kRqCands, 7)
+// MINB: resident CTAs per SM the register budget is sized for.  7 (128 registers: four warps per
+// sub-partition's 16 K registers) keeps a 1024-trajectory round in one wave; a launch of at most
+// 3 CTAs per SM (small batches, the strong split over 8 GPUs, later line-search rounds) takes the
+// 3-CTA build, which spills nothing on the serial path.
+template <bool SHARED, bool QUAT, int MINB>
+__global__ void __launch_bounds__(kRqLanes * kRqCands, MINB)
 rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   typedef Quadruped Qd;
   typedef RqLayout<QUAT> Ly;
