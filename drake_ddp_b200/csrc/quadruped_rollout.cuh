@@ -180,12 +180,11 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   if (SHARED) stage(0, 0);
 
   // diagonal cost: weights and targets of this lane's entries (states lane + 8k, controls lane + 8k)
-  double wq[5], wf[5], xn_[5], wr[2];
+  double wq[5], xn_[5], wr[2];   // (the terminal weights are fetched after the last step: ten registers less in the loop)
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const int j = lane + kRqLanes * k;
     wq[k] = (j < n) ? d.Q[j * n + j] : 0.0;
-    wf[k] = (j < n) ? d.Qf[j * n + j] : 0.0;
     xn_[k] = (j < n) ? xnom[j] : 0.0;
   }
 #pragma unroll
@@ -483,7 +482,8 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
       for (int k = 0; k < 5; ++k) {
         const int j = lane + kRqLanes * k;
         const double e = ((j < n) ? s.x[j] : 0.0) - xn_[k];
-        sacc = fma(wf[k] * e, e, sacc);
+        const double wfk = (j < n) ? d.Qf[j * n + j] : 0.0;
+        sacc = fma(wfk * e, e, sacc);
       }
     } else {
       for (int j = lane; j < n; j += kRqLanes) {
