@@ -37,6 +37,8 @@ struct RqCandSmem {
   double vn[18];    // staged v+ of the substep
   double acc[18];   // accelerations of the substep
   double u[12];     // controls of the step
+  double cw[12][8]; // per-lane constants of the diagonal cost: weights of its 5 state and 2 control entries, 5 targets
+                    // (24 registers that the 128-register build would spill and reload every step)
 };
 
 // state layout of the two base parameterisations and the layout of one staged step
@@ -180,17 +182,16 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
   if (SHARED) stage(0, 0);
 
   // diagonal cost: weights and targets of this lane's entries (states lane + 8k, controls lane + 8k)
-  double wq[5], xn_[5], wr[2];   // (the terminal weights are fetched after the last step: ten registers less in the loop)
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const int j = lane + kRqLanes * k;
-    wq[k] = (j < n) ? d.Q[j * n + j] : 0.0;
-    xn_[k] = (j < n) ? xnom[j] : 0.0;
+    s.cw[k][lane] = (j < n) ? d.Q[j * n + j] : 0.0;
+    s.cw[5 + k][lane] = (j < n) ? xnom[j] : 0.0;
   }
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int r = lane + kRqLanes * k;
-    wr[k] = (r < m) ? d.R[r * m + r] : 0.0;
+    s.cw[10 + k][lane] = (r < m) ? d.R[r * m + r] : 0.0;
   }
   // reciprocal mass / inertia of the base acceleration this lane computes (lanes 0..5), fetched once:
   // a ternary over global loads inside the step compiles to branches
@@ -270,14 +271,14 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int j = lane + kRqLanes * k;
-          const double e = ((j < n) ? s.x[j] : 0.0) - xn_[k];
-          pt[k] = (wq[k] * e) * e;
+          const double e = ((j < n) ? s.x[j] : 0.0) - s.cw[5 + k][lane];
+          pt[k] = (s.cw[k][lane] * e) * e;
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int r = lane + kRqLanes * k;
           const double uu = (r < m) ? s.u[r] : 0.0;
-          pt[5 + k] = (wr[k] * uu) * uu;
+          pt[5 + k] = (s.cw[10 + k][lane] * uu) * uu;
         }
         sacc = ((pt[0] + pt[1]) + (pt[2] + pt[3])) + ((pt[4] + pt[5]) + pt[6]);
       } else {
@@ -481,7 +482,7 @@ rollout_quad8_kernel(Dev d, int ls_base, int per_traj, int n_items) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const int j = lane + kRqLanes * k;
-        const double e = ((j < n) ? s.x[j] : 0.0) - xn_[k];
+        const double e = ((j < n) ? s.x[j] : 0.0) - s.cw[5 + k][lane];
         const double wfk = (j < n) ? d.Qf[j * n + j] : 0.0;
         sacc = fma(wfk * e, e, sacc);
       }
